@@ -1,0 +1,101 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes-facing C API over oracle/mccfr.hpp (tests, smoke and the
+// cpu_baseline leg of bench.py are the only permitted callers).
+#include <algorithm>
+#include <cstdio>
+
+#include "mccfr.hpp"
+
+using namespace orc;
+
+struct OrcSolver {
+    int game;  // 0 kuhn, 1 leduc
+    Solver<KuhnGame> kuhn;
+    Solver<LeducGame> leduc;
+};
+
+template <class F>
+static auto with(OrcSolver* s, F f) {
+    return s->game == 0 ? f(s->kuhn) : f(s->leduc);
+}
+
+extern "C" {
+
+struct OrcRow {
+    uint32_t info_key;
+    uint32_t action;
+    float weight, regret, payoff;
+    uint32_t visits;
+};
+
+void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    Philox4 p = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = p.r[i];
+}
+
+OrcSolver* orc_solver_create(int game, int regret, int weight, int sampling, int batch, uint64_t seed, int threads) {
+    if (game < 0 || game > 1) return nullptr;
+    OrcSolver* s = new OrcSolver();
+    s->game = game;
+    auto init = [&](auto& sv) {
+        sv.regret_sched = regret; sv.weight_sched = weight; sv.sampling = sampling;
+        sv.batch = batch; sv.threads = threads; sv.rng.seed = seed;
+        return 0;
+    };
+    with(s, init);
+    return s;
+}
+void orc_solver_destroy(OrcSolver* s) { delete s; }
+void orc_solver_step(OrcSolver* s, uint64_t n) {
+    with(s, [&](auto& sv) { for (uint64_t i = 0; i < n; ++i) sv.step(); return 0; });
+}
+uint64_t orc_solver_epochs(OrcSolver* s) { return with(s, [](auto& sv) { return sv.profile.epochs; }); }
+uint64_t orc_solver_updates(OrcSolver* s) { return with(s, [](auto& sv) { return sv.updates; }); }
+uint64_t orc_solver_nodes(OrcSolver* s) { return with(s, [](auto& sv) { return sv.nodes; }); }
+uint64_t orc_solver_infos(OrcSolver* s) { return with(s, [](auto& sv) { return sv.infos; }); }
+float orc_solver_exploitability(OrcSolver* s) { return with(s, [](auto& sv) { return sv.exploitability(nullptr); }); }
+void orc_solver_tree_stats(OrcSolver* s, int* out3) {
+    with(s, [&](auto& sv) {
+        typename std::decay_t<decltype(sv)>::ExplStats st{};
+        sv.exploitability(&st);
+        out3[0] = st.nodes; out3[1] = st.terminals; out3[2] = st.infosets;
+        return 0;
+    });
+}
+// rows sorted by (info_key, action); only rows that exist in the reference's HashMap sense
+int orc_solver_export(OrcSolver* s, OrcRow* out, int cap) {
+    return with(s, [&](auto& sv) {
+        std::vector<OrcRow> rows;
+        for (auto& kv : sv.profile.rows)
+            for (int a = 0; a < kv.second.n; ++a)
+                if (kv.second.present[a]) {
+                    const Encounter& e = kv.second.e[a];
+                    rows.push_back(OrcRow{kv.first, (uint32_t)a, e.weight, e.regret, e.payoff, e.visits});
+                }
+        std::sort(rows.begin(), rows.end(), [](const OrcRow& x, const OrcRow& y) {
+            return x.info_key != y.info_key ? x.info_key < y.info_key : x.action < y.action;
+        });
+        int n = (int)rows.size();
+        for (int i = 0; i < n && i < cap; ++i) out[i] = rows[i];
+        return n;
+    });
+}
+void orc_solver_import(OrcSolver* s, const OrcRow* in, int n, uint64_t epochs) {
+    with(s, [&](auto& sv) {
+        sv.profile.rows.clear();
+        for (int i = 0; i < n; ++i) {
+            Encounter& e = sv.profile.mut_row(in[i].info_key, (int)in[i].action);
+            e = Encounter{in[i].weight, in[i].regret, in[i].payoff, in[i].visits};
+        }
+        sv.profile.epochs = epochs;
+        return 0;
+    });
+}
+// averaged policy (Nash approximation) for one infoset: profile.rs:41-45
+int orc_solver_averaged(OrcSolver* s, uint32_t info_key, float* out) {
+    return with(s, [&](auto& sv) {
+        auto v = sv.averaged(info_key);
+        for (int a = 0; a < v.n; ++a) out[a] = v.p[a];
+        return v.n;
+    });
+}
+}
