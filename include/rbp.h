@@ -1,0 +1,128 @@
+/* rbp.h — C ABI of librbp_b200.so: the B200-native (sm_100a) drop-in for robopoker's data-parallel
+ * training path.  Every entry point cites the reference seam it replaces (paths relative to the
+ * krukah/robopoker checkout).  Plain pointers and sizes only; the library owns all device state
+ * behind opaque handles; every call is synchronous with respect to the HOST buffers it is given.
+ * All functions return RBP_OK (0) or a negative status; the reference's convention on this path is
+ * to panic (`expect`) — the Rust shim in INTEGRATION.md panics on any non-zero status.
+ * There is no CPU fallback: every compute entry point fails with RBP_ERR_NO_DEVICE without a GPU.
+ */
+#ifndef RBP_H
+#define RBP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    RBP_OK = 0,
+    RBP_ERR_INVALID = -1,    /* bad argument / unknown enum */
+    RBP_ERR_NO_DEVICE = -2,  /* no CUDA device (the library never computes on the CPU) */
+    RBP_ERR_CUDA = -3,       /* a CUDA call failed; see rbp_last_error() */
+    RBP_ERR_CAPACITY = -4,   /* game / buffer exceeds a compiled-in or caller-provided capacity */
+    RBP_ERR_STATE = -5       /* call sequence error (e.g. step before init) */
+};
+const char* rbp_status_string(int status);
+const char* rbp_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+uint64_t rbp_kernel_launches(void);
+int rbp_device_count(void);
+
+/* ─────────────────────────────── MCCFR ─────────────────────────────── */
+
+/* crates/mccfr/src/solver/encounter.rs:21-27 — one (infoset, action) row, 16 B, same field order */
+typedef struct {
+    float weight;
+    float regret;
+    float payoff;
+    uint32_t visits;
+} rbp_encounter_t;
+
+/* Row as exchanged with the host: key = (packed infoset key, action index in `choices()` order).
+ * Packed infoset keys (also a Philox counter word of the RNG contract below):
+ *   Kuhn  (crates/kuhn/src/info.rs:9-76):   bit0 acting | bits1-2 History{Open,Check,Bet,CheckBet} | bits3-4 Rank{J,Q,K}
+ *   Leduc (crates/leduc/src/info.rs:12-94): bit0 acting | bits1-2 board (0 none, 1+Rank) | bits3-4 r1 Spot
+ *                                           | bits5-7 r2 (0 none, 1+Spot) | bits8-9 own Rank
+ *   Spot = {Open,Checked,Raised,CheckRaised} (crates/leduc/src/game.rs:6-11)                            */
+typedef struct {
+    uint32_t info_key;
+    uint32_t action;
+    rbp_encounter_t row;
+} rbp_profile_row_t;
+
+/* generic choices R, W, S of `trait Solver` (crates/mccfr/src/solver/solver.rs:38-74) as enums */
+enum { RBP_GAME_KUHN = 0, RBP_GAME_LEDUC = 1 };
+enum { RBP_REGRET_SUMMED = 0, RBP_REGRET_FLOORED = 1, RBP_REGRET_LINEAR = 2, RBP_REGRET_DISCOUNTED = 3, RBP_REGRET_ASYMMETRIC = 4 }; /* crates/mccfr/src/regret/*.rs */
+enum { RBP_WEIGHT_CONSTANT = 0, RBP_WEIGHT_LINEAR = 1, RBP_WEIGHT_QUADRATIC = 2, RBP_WEIGHT_EXPONENTIAL = 3 };                       /* crates/mccfr/src/policy/*.rs */
+enum { RBP_SAMPLING_EXTERNAL = 0, RBP_SAMPLING_VANILLA = 1, RBP_SAMPLING_PRUNABLE = 2, RBP_SAMPLING_PLURIBUS = 3 };                  /* crates/mccfr/src/sample/*.rs */
+/* how the per-tree Decisions of one epoch are folded into the table:
+ *   ORDERED — reference semantics (solver.rs:96-105): one schedule application per Decisions, in tree order.
+ *   BATCHED — one schedule application per row per epoch on the blocked-order sum of the deltas
+ *             (the "allreduce of deltas" form; identical to ORDERED at batch 1).                       */
+enum { RBP_FOLD_ORDERED = 0, RBP_FOLD_BATCHED = 1 };
+
+/* process-global hyper-parameter singletons of the reference, as one POD:
+ * crates/mccfr/src/hyperparams/{sampling.rs:39-50, pruning.rs:40-55, training.rs:52-60} */
+typedef struct {
+    float temperature;     /* 1.0  */
+    float smoothing;       /* 2.0  */
+    float curiosity;       /* 0.05 */
+    float prune_threshold; /* -3e5 */
+    float prune_explore;   /* 0.05 */
+    uint32_t prune_warmup; /* 16384 */
+    float regret_min;      /* -4e6 */
+} rbp_hyper_t;
+void rbp_hyper_default(rbp_hyper_t* out);
+
+/* RNG contract (replaces SipHash+SmallRng of crates/mccfr/src/strategy/flow.rs:285-295 and the thread RNG
+ * of `CfrGame::root`): Philox4x32-10, key=(seed_lo,seed_hi), counter=(epoch, tree_id, info_key, tag),
+ * tag 0 node draw / 1 root deal (info_key 0xFFFFFFFF) / 2 pluribus coin;
+ * range(n)=(u64(r0)*n)>>32; unit=(r0>>8)*2^-24; weighted = first i with unit*Σw < Σ_{j<=i}w_j (sequential f32). */
+void rbp_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
+typedef struct rbp_solver rbp_solver_t;
+
+/* `Kuhn::<R,W,S>::default()` / `Leduc::<R,W,S>::default()` (crates/mccfr/src/strategy/macros.rs:7-151) with
+ * `batch_size()` = batch.  `world_rank/world_size` shard the trees of an epoch: this handle samples tree ids
+ * [rank*batch, (rank+1)*batch) of a global batch of world_size*batch trees (see rbp_solver_* exchange calls). */
+int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_mode, int batch, uint64_t seed,
+                      const rbp_hyper_t* hyper /* NULL = defaults */, int device, rbp_solver_t** out);
+int rbp_solver_set_world(rbp_solver_t* s, int world_rank, int world_size);
+void rbp_solver_destroy(rbp_solver_t* s);
+/* `Solver::step` ×n (solver.rs:96-105) — sample `batch` trees, compute Decisions, fold, advance epoch */
+int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs);
+/* rbp_solver_step with CUDA-event timing on the library's own stream (bench.py): every epoch is bracketed by
+ * events, optionally preceded by an (untimed) L2 flush; returns the summed device milliseconds of the n steps and,
+ * if non-NULL, the summed durations of the sampling and fold kernels. */
+int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, float* ms_total, float* ms_sample, float* ms_fold);
+/* `RefProf::t` (crates/mccfr/src/strategy/profile.rs:14) */
+int rbp_solver_epochs(rbp_solver_t* s, uint64_t* out);
+/* `Solver::exploitability` (solver.rs:327-338 → crates/mccfr/src/strategy/nash.rs:31-193) */
+int rbp_solver_exploitability(rbp_solver_t* s, float* out);
+/* telemetry of crates/mccfr/src/metrics/mod.rs: [0] nodes, [1] infosets (Decisions), [2] infoset-action regret updates */
+int rbp_solver_counters(rbp_solver_t* s, uint64_t out[3]);
+/* bulk forms of `RefProf::cum_*` / `MutProf::mut_*` / `CfrData::encounters_{ref,mut}`
+ * (crates/mccfr/src/strategy/{profile.rs:12-25,storage.rs,book.rs:14-24}).  Export returns the rows the
+ * reference's HashMap would hold (touched rows), sorted by (info_key, action). */
+int rbp_profile_export(rbp_solver_t* s, rbp_profile_row_t* rows, int cap, int* n_out);
+int rbp_profile_import(rbp_solver_t* s, const rbp_profile_row_t* rows, int n, uint64_t epochs);
+/* `RefProf::averaged_distribution` (profile.rs:41-45) for one infoset; returns n actions in *n_out */
+int rbp_profile_averaged(rbp_solver_t* s, uint32_t info_key, float* probs, int cap, int* n_out);
+/* shape of the enumerated game: [0] nodes, [1] terminals, [2] decision infosets, [3] rows,
+ * [4] max nodes of a sampled tree, [5] max walker infosets per sampled tree */
+int rbp_solver_game_shape(rbp_solver_t* s, int out[6]);
+
+/* Multi-GPU exchange (one process per GPU).  The library does not link a collective library: the host
+ * (Rust shim / torch.distributed) moves these device buffers with NCCL.  BATCHED fold: after
+ * rbp_solver_sample() each rank holds its blocked partial sums; all-gather `delta` buffers across ranks into
+ * `gathered` (rank-major) and call rbp_solver_fold_gathered(), which sums in rank order — bit-identical on
+ * every rank and to the single-GPU run with world_size*batch trees. */
+int rbp_solver_sample(rbp_solver_t* s);                                   /* K1 only (+ local blocked sums)     */
+int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes); /* this rank's partial sums (device) */
+int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size); /* K2 over all ranks  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBP_H */

@@ -1,0 +1,109 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes wrapper over oracle/build/librbp_oracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "build", "librbp_oracle.so")
+
+ROW_DTYPE = np.dtype([("info_key", "<u4"), ("action", "<u4"), ("weight", "<f4"), ("regret", "<f4"), ("payoff", "<f4"),
+                      ("visits", "<u4")])
+GAMES = {"kuhn": 0, "leduc": 1}
+REGRETS = {"SummedRegret": 0, "FlooredRegret": 1, "LinearRegret": 2, "DiscountedRegret": 3, "AsymmetricRegret": 4}
+WEIGHTS = {"ConstantWeight": 0, "LinearWeight": 1, "QuadraticWeight": 2, "ExponentialWeight": 3}
+SAMPLERS = {"ExternalSampling": 0, "VanillaSampling": 1, "PrunableSampling": 2, "PluribusSampling": 3}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} missing: run __graft_entry__.build()")
+        l = ctypes.CDLL(LIB_PATH)
+        vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
+        l.orc_solver_create.restype = vp
+        l.orc_solver_create.argtypes = [i32, i32, i32, i32, i32, u64, i32]
+        l.orc_solver_destroy.argtypes = [vp]
+        l.orc_solver_step.argtypes = [vp, u64]
+        for f in ("epochs", "updates", "nodes", "infos"):
+            getattr(l, "orc_solver_" + f).restype = u64
+            getattr(l, "orc_solver_" + f).argtypes = [vp]
+        l.orc_solver_exploitability.restype = ctypes.c_float
+        l.orc_solver_exploitability.argtypes = [vp]
+        l.orc_solver_tree_stats.argtypes = [vp, ctypes.POINTER(i32)]
+        l.orc_solver_export.argtypes = [vp, vp, i32]
+        l.orc_solver_import.argtypes = [vp, vp, i32, u64]
+        l.orc_solver_averaged.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_float)]
+        l.orc_solver_set_hyper.argtypes = [vp] + [ctypes.c_float] * 5 + [u32, ctypes.c_float]
+        l.orc_philox.argtypes = [u32] * 6 + [ctypes.POINTER(u32)]
+        _lib = l
+    return _lib
+
+
+def philox(counter, key):
+    out = (ctypes.c_uint32 * 4)()
+    lib().orc_philox(*counter, *key, out)
+    return list(out)
+
+
+class OracleSolver:
+    def __init__(self, game, regret="FlooredRegret", weight="LinearWeight", sampling="ExternalSampling", batch=1, seed=0, threads=1):
+        self.batch = batch
+        self._h = lib().orc_solver_create(GAMES[game], REGRETS[regret], WEIGHTS[weight], SAMPLERS[sampling], batch, seed, threads)
+        if not self._h:
+            raise ValueError("orc_solver_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_solver_destroy(self._h)
+            self._h = None
+
+    def set_hyper(self, **kw):
+        h = dict(temperature=1.0, smoothing=2.0, curiosity=0.05, prune_threshold=-3e5, prune_explore=0.05, prune_warmup=16384,
+                 regret_min=-4e6)
+        h.update(kw)
+        lib().orc_solver_set_hyper(self._h, h["temperature"], h["smoothing"], h["curiosity"], h["prune_threshold"],
+                                   h["prune_explore"], h["prune_warmup"], h["regret_min"])
+
+    def step(self, n=1):
+        lib().orc_solver_step(self._h, n)
+        return self
+
+    def solve(self, trees):
+        return self.step(trees // self.batch)
+
+    @property
+    def epochs(self):
+        return lib().orc_solver_epochs(self._h)
+
+    def counters(self):
+        l = lib()
+        return {"nodes": l.orc_solver_nodes(self._h), "infos": l.orc_solver_infos(self._h), "updates": l.orc_solver_updates(self._h)}
+
+    def exploitability(self):
+        return lib().orc_solver_exploitability(self._h)
+
+    def tree_stats(self):
+        out = (ctypes.c_int * 3)()
+        lib().orc_solver_tree_stats(self._h, out)
+        return {"nodes": out[0], "terminals": out[1], "infosets": out[2]}
+
+    def profile_rows(self):
+        buf = np.zeros(4096, dtype=ROW_DTYPE)
+        n = lib().orc_solver_export(self._h, buf.ctypes.data, len(buf))
+        return buf[:n]
+
+    def import_rows(self, rows, epochs):
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        lib().orc_solver_import(self._h, rows.ctypes.data, len(rows), epochs)
+
+    def averaged_distribution(self, info_key):
+        out = (ctypes.c_float * 8)()
+        n = lib().orc_solver_averaged(self._h, info_key, out)
+        return [out[i] for i in range(n)]

@@ -90,6 +90,13 @@ void orc_solver_import(OrcSolver* s, const OrcRow* in, int n, uint64_t epochs) {
         return 0;
     });
 }
+void orc_solver_set_hyper(OrcSolver* s, float temperature, float smoothing, float curiosity, float prune_threshold,
+                          float prune_explore, uint32_t prune_warmup, float regret_min) {
+    with(s, [&](auto& sv) {
+        sv.profile.hyper = Hyper{temperature, smoothing, curiosity, prune_threshold, prune_explore, prune_warmup, regret_min};
+        return 0;
+    });
+}
 // averaged policy (Nash approximation) for one infoset: profile.rs:41-45
 int orc_solver_averaged(OrcSolver* s, uint32_t info_key, float* out) {
     return with(s, [&](auto& sv) {

@@ -1,0 +1,78 @@
+"""ctypes binding of include/rbp.h.  Fails loudly when the CUDA extension is missing — never falls back."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librbp_b200.so")
+
+
+class RbpError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        l = load_library()
+        msg = l.rbp_status_string(status).decode()
+        detail = l.rbp_last_error().decode()
+        super().__init__(f"{where}: {msg} ({status}) {detail}")
+
+
+class Encounter(ctypes.Structure):
+    _fields_ = [("weight", ctypes.c_float), ("regret", ctypes.c_float), ("payoff", ctypes.c_float), ("visits", ctypes.c_uint32)]
+
+
+class ProfileRow(ctypes.Structure):
+    _fields_ = [("info_key", ctypes.c_uint32), ("action", ctypes.c_uint32), ("row", Encounter)]
+
+
+class HyperC(ctypes.Structure):
+    _fields_ = [("temperature", ctypes.c_float), ("smoothing", ctypes.c_float), ("curiosity", ctypes.c_float),
+                ("prune_threshold", ctypes.c_float), ("prune_explore", ctypes.c_float), ("prune_warmup", ctypes.c_uint32),
+                ("regret_min", ctypes.c_float)]
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(librbp_b200 has no CPU fallback)")
+    l = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
+    P = ctypes.POINTER
+    l.rbp_status_string.restype = ctypes.c_char_p
+    l.rbp_status_string.argtypes = [i32]
+    l.rbp_last_error.restype = ctypes.c_char_p
+    l.rbp_kernel_launches.restype = u64
+    l.rbp_device_count.restype = i32
+    l.rbp_hyper_default.argtypes = [P(HyperC)]
+    l.rbp_philox4x32_10.argtypes = [P(u32), P(u32), P(u32)]
+    l.rbp_solver_create.argtypes = [i32, i32, i32, i32, i32, i32, u64, P(HyperC), i32, P(vp)]
+    l.rbp_solver_set_world.argtypes = [vp, i32, i32]
+    l.rbp_solver_destroy.argtypes = [vp]
+    l.rbp_solver_destroy.restype = None
+    l.rbp_solver_step.argtypes = [vp, u64]
+    l.rbp_solver_step_timed.argtypes = [vp, u64, i32, P(ctypes.c_float), P(ctypes.c_float), P(ctypes.c_float)]
+    l.rbp_solver_epochs.argtypes = [vp, P(u64)]
+    l.rbp_solver_exploitability.argtypes = [vp, P(ctypes.c_float)]
+    l.rbp_solver_counters.argtypes = [vp, P(u64)]
+    l.rbp_profile_export.argtypes = [vp, P(ProfileRow), i32, P(i32)]
+    l.rbp_profile_import.argtypes = [vp, P(ProfileRow), i32, u64]
+    l.rbp_profile_averaged.argtypes = [vp, u32, P(ctypes.c_float), i32, P(i32)]
+    l.rbp_solver_game_shape.argtypes = [vp, P(i32)]
+    l.rbp_solver_sample.argtypes = [vp]
+    l.rbp_solver_delta_buffer.argtypes = [vp, P(vp), P(ctypes.c_size_t)]
+    l.rbp_solver_fold_gathered.argtypes = [vp, vp, i32]
+    _lib = l
+    return l
+
+
+def lib():
+    return load_library()
+
+
+def check(status, where):
+    if status != 0:
+        raise RbpError(status, where)

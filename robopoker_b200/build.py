@@ -1,0 +1,71 @@
+"""In-tree build of librbp_b200.so (sm_100a only) and of the oracle's C++ restatement.
+
+nvcc cross-compiles without a GPU; the .so files travel to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "robopoker_b200", "csrc")
+LIB = os.path.join(ROOT, "robopoker_b200", "librbp_b200.so")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "build", "librbp_oracle.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+# per-source flags: kernels whose results must be bit-identical to the oracle's strict f32 arithmetic are
+# compiled without FMA contraction and with IEEE division/sqrt (nvcc defaults: -prec-div=true -prec-sqrt=true -ftz=false)
+SOURCES = {
+    "flat_game.cpp": ["-Xcompiler", "-ffp-contract=off"],
+    "mccfr.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
+}
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + "\n")
+        raise RuntimeError("build failed: " + " ".join(cmd[:3]))
+    return r.stdout
+
+
+def build_lib(force=False, verbose=False):
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "rbp.h"))
+    objs = []
+    for src, flags in SOURCES.items():
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        if force or not _newer(obj, [path] + headers):
+            out = _run([NVCC] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj])
+            if verbose:
+                print(out)
+        objs.append(obj)
+    if force or not _newer(LIB, objs):
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith(".cpp")]
+    deps = srcs + [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".hpp")]
+    os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
+    if force or not _newer(ORACLE_LIB, deps):
+        _run(["g++", "-std=c++17", "-O2", "-march=x86-64-v2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+              "-o", ORACLE_LIB] + srcs)
+    return ORACLE_LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_oracle(force="--force" in sys.argv))

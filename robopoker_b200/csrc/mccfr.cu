@@ -1,0 +1,855 @@
+// mccfr.cu — external-sampling MCCFR for flat games on sm_100a, and its C ABI (include/rbp.h).
+//
+// One epoch (= one `Solver::step`, crates/mccfr/src/solver/solver.rs:96-105) is two kernels:
+//
+//   mccfr_sample_kernel   one thread per tree.  Restates `Solver::batch` (solver.rs:225-240): deal the root,
+//                         grow the sampled tree in the reference's LIFO order (solver/builder.rs:74-161) with
+//                         External / Prunable / Pluribus sampling (sample/*.rs), then for every walker infoset
+//                         the fused regret+value pass `CfrFlow::dfs` (strategy/flow.rs:64-87,166-216) with the
+//                         reference's exact f32 operation order (compiled -fmad=false), producing `Decisions`
+//                         records.  The block then stably multisplits its records by infoset (smem lane bitmaps
+//                         → ranks) so that each infoset's records are contiguous and in tree order.
+//   mccfr_fold_kernel     one warp per infoset, one lane per (row, field) chain.  Restates the serial fold of
+//                         `update_regret/weight/payoff/visits` (solver.rs:143-192): every Decisions is applied
+//                         in tree order with the schedule of regret/*.rs and policy/*.rs.  Rows are 16-byte
+//                         `Encounter`s resident in HBM (L2-resident for the validation games).
+//
+// Because every f32 operation and its order match the oracle's, results are bit-identical, so the sampled
+// trajectories of GPU and oracle never diverge.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "flat_game.hpp"
+
+namespace rbp {
+
+std::atomic<uint64_t> g_launches{0};
+static std::mutex g_err_mu;
+static std::string g_err;
+void set_last_error(const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = msg;
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
+    set_last_error(buf);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RBP_ERR_NO_DEVICE : RBP_ERR_CUDA;
+}
+
+// ───────────────────────────── device-side views ─────────────────────────────
+constexpr int kTreesPerBlock = 128;
+constexpr int kMaxTreeNodes = 48;   // local sampled-tree capacity (Leduc needs 29)
+constexpr int kMaxDepth = 16;
+constexpr int kMaxRecords = 8;      // walker infosets per sampled tree (Leduc needs 7)
+constexpr int kMaxInfos = 512;      // smem-resident infoset views
+
+struct DevGame {
+    const FlatNode* nodes;
+    const float* payoff1;
+    const int32_t* root_table;
+    const int32_t* info_row;
+    const uint8_t* info_actions;
+    const uint8_t* info_player;
+    const int32_t* parent;
+    const int32_t* level_start;
+    const int32_t* span_start;
+    const int32_t* span_nodes;
+    int n_nodes, n_infos, n_rows, n_levels, deck;
+};
+
+struct Scratch {        // per-epoch Decisions, block-sorted by infoset
+    float* pay;         // [nblk * cap]
+    float* dr;          // [kMaxActions][nblk * cap]
+    uint8_t* mask;      // [nblk * cap] explored bits
+    int32_t* m_off;     // [I][nblk]
+    int32_t* m_cnt;     // [I][nblk]
+    unsigned long long* counters;  // nodes, infos, updates
+    int nblk, cap;      // cap = records per block
+};
+
+struct EpochArgs {
+    uint32_t seed_lo, seed_hi, epoch;
+    int walker, batch, tree_base, sampling;
+    rbp_hyper_t hyper;
+    int regret_sched, weight_sched;
+    float t;                // epoch as f32
+    float disc_pos, disc_neg;  // DiscountedRegret x = t^1.5, t^0.5 (host libm, regret/discounted.rs:33,37)
+};
+
+__device__ __forceinline__ float fmax_ref(float a, float b) { return a > b ? a : b; }
+
+// ───────────────────────────── K1: sample + value + multisplit ─────────────────────────────
+__global__ void __launch_bounds__(kTreesPerBlock)
+mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratch sc, EpochArgs ep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int I = g.n_infos;
+    float* s_sigma = reinterpret_cast<float*>(smem_raw);        // [I][4]  regret-matching policy
+    float* s_q = s_sigma + I * kMaxActions;                     // [I][4]  sampling distribution
+    float* s_cumr = s_q + I * kMaxActions;                      // [I][4]  raw cumulative regret (pruning)
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_cumr + I * kMaxActions);  // [4][I] lane bitmaps
+    uint32_t* s_woff = s_bits + 4 * I;                          // [4][I] warp offsets
+    uint32_t* s_cnt = s_woff + 4 * I;                           // [I]
+    uint32_t* s_off = s_cnt + I;                                // [I]
+    __shared__ uint32_t s_scan[kTreesPerBlock / 32 + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // infoset views (strategy/profile.rs:31-51, flow.rs:20-59), once per block instead of once per node visit
+    for (int x = tid; x < I; x += kTreesPerBlock) {
+        const int A = g.info_actions[x], row = g.info_row[x];
+        float r[kMaxActions], w[kMaxActions], sw[kMaxActions];
+        float rd = 0.0f, ws = 0.0f;
+        for (int a = 0; a < A; ++a) {
+            rbp_encounter_t e = table[row + a];
+            s_cumr[x * kMaxActions + a] = e.regret;
+            r[a] = fmax_ref(e.regret, kEps);
+            rd = rd + r[a];
+            w[a] = fmax_ref(e.weight, kEps);
+            ws = ws + w[a];
+        }
+        const float denom = ws + ep.hyper.smoothing;
+        float z = 0.0f;
+        for (int a = 0; a < A; ++a) {
+            float s = (w[a] / ep.hyper.temperature + ep.hyper.smoothing) / denom;
+            sw[a] = fmax_ref(s, ep.hyper.curiosity);
+            z = z + sw[a];
+        }
+        for (int a = 0; a < A; ++a) {
+            s_sigma[x * kMaxActions + a] = r[a] / rd;
+            s_q[x * kMaxActions + a] = sw[a] / z;
+        }
+        for (int wv = 0; wv < 4; ++wv) s_bits[wv * I + x] = 0u;
+    }
+    __syncthreads();
+
+    const int local = blockIdx.x * kTreesPerBlock + tid;
+    const bool active = local < ep.batch;
+    const uint32_t tree = (uint32_t)(ep.tree_base + local);
+
+    // Decisions of this tree
+    int nrec = 0;
+    int16_t rec_info[kMaxRecords];
+    uint8_t rec_mask[kMaxRecords];
+    float rec_pay[kMaxRecords];
+    float rec_dr[kMaxRecords][kMaxActions];
+    int ln = 0;
+
+    if (active) {
+        // sampled tree, reference node order (petgraph-style adjacency: head = newest child)
+        int16_t l_flat[kMaxTreeNodes];
+        int8_t l_parent[kMaxTreeNodes], l_act[kMaxTreeNodes], l_head[kMaxTreeNodes], l_next[kMaxTreeNodes];
+        int16_t t_flat[kMaxTreeNodes];
+        int8_t t_parent[kMaxTreeNodes], t_act[kMaxTreeNodes];
+        int tn = 0;
+
+        // `CfrGame::root()` (kuhn/leduc game.rs root()): two-swap Fisher-Yates of the identity deck
+        {
+            Philox4 pr = philox4x32_10(ep.epoch, tree, 0xFFFFFFFFu, TAG_ROOT, ep.seed_lo, ep.seed_hi);
+            uint32_t i = draw_range(pr.r[0], (uint32_t)g.deck);
+            uint32_t j = 1u + draw_range(pr.r[1], (uint32_t)g.deck - 1u);
+            uint32_t c0 = i, c1 = (j == i) ? 0u : j;
+            l_flat[0] = (int16_t)g.root_table[c0 * g.deck + c1];
+            l_parent[0] = -1; l_act[0] = 0; l_head[0] = -1; l_next[0] = -1;
+            ln = 1;
+        }
+        // S::sample + encoder.branches for local node k (sample/{external,pruning,pluribus}.rs)
+        auto expand = [&](int k) {
+            const FlatNode nd = g.nodes[l_flat[k]];
+            const int n = nd.n_child;
+            if (n == 0) return;
+            if (nd.turn == ep.walker) {
+                uint32_t keep = (1u << n) - 1u;
+                bool prune = ep.sampling == RBP_SAMPLING_PRUNABLE;
+                if (ep.sampling == RBP_SAMPLING_PLURIBUS && ep.epoch >= ep.hyper.prune_warmup) {
+                    Philox4 pc = philox4x32_10(ep.epoch, tree, nd.info_key, TAG_COIN, ep.seed_lo, ep.seed_hi);
+                    prune = !(draw_unit(pc.r[0]) < ep.hyper.prune_explore);
+                }
+                if (prune) {
+                    uint32_t kept = 0;
+                    for (int a = 0; a < n; ++a) {
+                        bool ok = s_cumr[nd.info * kMaxActions + a] > ep.hyper.prune_threshold;
+                        if (ep.sampling == RBP_SAMPLING_PLURIBUS && g.nodes[nd.first_child + a].turn == TURN_TERMINAL) ok = true;
+                        if (ok) kept |= 1u << a;
+                    }
+                    if (kept) keep = kept;
+                }
+                for (int a = 0; a < n; ++a)
+                    if (keep >> a & 1u) { t_flat[tn] = (int16_t)(nd.first_child + a); t_parent[tn] = (int8_t)k; t_act[tn] = (int8_t)a; ++tn; }
+                return;
+            }
+            Philox4 p = philox4x32_10(ep.epoch, tree, nd.info_key, TAG_NODE, ep.seed_lo, ep.seed_hi);
+            int pick;
+            if (nd.turn == TURN_CHANCE) {
+                pick = (int)draw_range(p.r[0], (uint32_t)n);  // sample/mod.rs:68-82
+            } else {  // sample/external.rs:42-64
+                const float* q = s_q + nd.info * kMaxActions;
+                float total = 0.0f;
+                for (int a = 0; a < n; ++a) total = total + fmax_ref(q[a], kEps);
+                const float x = draw_unit(p.r[0]) * total;
+                float cum = 0.0f;
+                pick = n - 1;
+                for (int a = 0; a < n; ++a) {
+                    cum = cum + fmax_ref(q[a], kEps);
+                    if (x < cum) { pick = a; break; }
+                }
+            }
+            t_flat[tn] = (int16_t)(nd.first_child + pick); t_parent[tn] = (int8_t)k; t_act[tn] = (int8_t)pick; ++tn;
+        };
+        expand(0);
+        while (tn > 0) {  // builder.rs:141-160: pop the newest branch
+            --tn;
+            const int k = ln++;
+            const int par = t_parent[tn];
+            l_flat[k] = t_flat[tn]; l_parent[k] = (int8_t)par; l_act[k] = t_act[tn];
+            l_head[k] = -1; l_next[k] = l_head[par]; l_head[par] = (int8_t)k;
+            expand(k);
+        }
+
+        // flow.rs:64-87 dfs over every walker node, node-index order
+        const int hero = ep.walker;
+        for (int k = 0; k < ln; ++k) {
+            const FlatNode nd = g.nodes[l_flat[k]];
+            if (nd.turn != hero || l_head[k] < 0) continue;
+            // ancestor_reach (flow.rs:166-174): upward over non-walker decision ancestors
+            float cf = 1.0f, sm = 1.0f;
+            for (int node = k; l_parent[node] >= 0; node = l_parent[node]) {
+                const FlatNode pn = g.nodes[l_flat[l_parent[node]]];
+                if (pn.turn <= TURN_P1 && pn.turn != hero) {
+                    cf = cf * s_sigma[pn.info * kMaxActions + l_act[node]];
+                    sm = sm * s_q[pn.info * kMaxActions + l_act[node]];
+                }
+            }
+            const float reach = cf / sm;
+            float val[kMaxActions];
+            int act[kMaxActions], nk = 0;
+            for (int c0 = l_head[k]; c0 >= 0; c0 = l_next[c0]) {
+                // recursed_value(root, child, 1, 1) (flow.rs:182-216), explicit stack
+                int s_node[kMaxDepth], s_it[kMaxDepth];
+                float s_rel[kMaxDepth], s_smp[kMaxDepth], s_acc[kMaxDepth];
+                int sp = 0;
+                s_node[0] = c0; s_it[0] = l_head[c0]; s_rel[0] = 1.0f; s_smp[0] = 1.0f; s_acc[0] = 0.0f;
+                float ret = 0.0f;
+                while (true) {
+                    const int n = s_node[sp];
+                    bool done = false;
+                    if (l_head[n] < 0) {  // nash.rs:66-79 terminal_value
+                        const int fn = l_flat[n];
+                        const float u = hero == 0 ? g.nodes[fn].payoff0 : g.payoff1[fn];
+                        ret = s_rel[sp] / s_smp[sp] * u;
+                        done = true;
+                    } else if (s_it[sp] < 0) {
+                        ret = s_acc[sp];
+                        done = true;
+                    }
+                    if (done) {
+                        if (sp == 0) break;
+                        --sp;
+                        s_acc[sp] = s_acc[sp] + ret;
+                        continue;
+                    }
+                    const int c = s_it[sp];
+                    s_it[sp] = l_next[c];
+                    const FlatNode pn = g.nodes[l_flat[n]];
+                    float r2 = s_rel[sp], s2 = s_smp[sp];
+                    if (pn.turn <= TURN_P1) {
+                        r2 = r2 * s_sigma[pn.info * kMaxActions + l_act[c]];
+                        if (pn.turn != hero) s2 = s2 * s_q[pn.info * kMaxActions + l_act[c]];
+                    }
+                    ++sp;
+                    s_node[sp] = c; s_it[sp] = l_head[c]; s_rel[sp] = r2; s_smp[sp] = s2; s_acc[sp] = 0.0f;
+                }
+                act[nk] = l_act[c0];
+                val[nk] = reach * ret;
+                ++nk;
+            }
+            const float* sg = s_sigma + nd.info * kMaxActions;
+            float ev = 0.0f;
+            for (int i = 0; i < nk; ++i) ev = ev + sg[act[i]] * val[i];
+            int slot = 0;
+            for (; slot < nrec; ++slot) if (rec_info[slot] == nd.info) break;
+            if (slot == nrec) {
+                rec_info[slot] = nd.info; rec_mask[slot] = 0; rec_pay[slot] = 0.0f;
+                for (int a = 0; a < kMaxActions; ++a) rec_dr[slot][a] = 0.0f;
+                ++nrec;
+            }
+            rec_pay[slot] += ev;
+            for (int i = 0; i < nk; ++i) {
+                rec_dr[slot][act[i]] += val[i] - ev;
+                rec_mask[slot] |= (uint8_t)(1u << act[i]);
+            }
+        }
+    }
+
+    // ── stable multisplit of the block's records by infoset (tree order preserved) ──
+    for (int s = 0; s < nrec; ++s) atomicOr(&s_bits[warp * I + rec_info[s]], 1u << lane);
+    __syncthreads();
+    for (int x = tid; x < I; x += kTreesPerBlock) {
+        uint32_t run = 0;
+        for (int wv = 0; wv < 4; ++wv) {
+            s_woff[wv * I + x] = run;
+            run += __popc(s_bits[wv * I + x]);
+        }
+        s_cnt[x] = run;
+    }
+    __syncthreads();
+    // exclusive scan of s_cnt over infosets → s_off (warp 0, 32 infosets per step)
+    if (warp == 0) {
+        uint32_t carry = 0;
+        for (int base = 0; base < I; base += 32) {
+            const int x = base + lane;
+            const uint32_t v = x < I ? s_cnt[x] : 0u;
+            uint32_t inc = v;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += up;
+            }
+            if (x < I) s_off[x] = carry + inc - v;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) s_scan[0] = carry;
+    }
+    __syncthreads();
+    const size_t total = (size_t)sc.nblk * sc.cap;
+    const size_t base = (size_t)blockIdx.x * sc.cap;
+    for (int s = 0; s < nrec; ++s) {
+        const int x = rec_info[s];
+        const uint32_t bits = s_bits[warp * I + x];
+        const uint32_t pos = s_off[x] + s_woff[warp * I + x] + __popc(bits & ((1u << lane) - 1u));
+        sc.pay[base + pos] = rec_pay[s];
+        sc.mask[base + pos] = rec_mask[s];
+        const int A = g.info_actions[x];
+        for (int a = 0; a < A; ++a) sc.dr[(size_t)a * total + base + pos] = rec_dr[s][a];
+    }
+    for (int x = tid; x < I; x += kTreesPerBlock) {
+        sc.m_off[(size_t)x * sc.nblk + blockIdx.x] = (int32_t)s_off[x];
+        sc.m_cnt[(size_t)x * sc.nblk + blockIdx.x] = (int32_t)s_cnt[x];
+    }
+    // telemetry (metrics/mod.rs): nodes, infosets
+    unsigned long long nn = (unsigned long long)ln, ni = (unsigned long long)nrec;
+    for (int d = 16; d > 0; d >>= 1) {
+        nn += __shfl_down_sync(0xFFFFFFFFu, nn, d);
+        ni += __shfl_down_sync(0xFFFFFFFFu, ni, d);
+    }
+    if (lane == 0) {
+        atomicAdd(&sc.counters[0], nn);
+        atomicAdd(&sc.counters[1], ni);
+    }
+}
+
+// ───────────────────────────── K3: ordered fold ─────────────────────────────
+__device__ __forceinline__ float regret_gain(const EpochArgs& ep, float net, float add) {
+    float acc, floor = ep.hyper.regret_min;
+    switch (ep.regret_sched) {
+        case RBP_REGRET_SUMMED: acc = net + add; floor = -INFINITY; break;
+        case RBP_REGRET_FLOORED: acc = net + add; floor = 0.0f; break;
+        case RBP_REGRET_LINEAR: { float d = ep.t / (ep.t + 1.0f); acc = net * d + add; break; }
+        case RBP_REGRET_DISCOUNTED: {
+            float x = net > 0.0f ? ep.disc_pos : (net < 0.0f ? ep.disc_neg : ep.t);
+            float d = x / (x + 1.0f);
+            acc = net * d + add;
+            break;
+        }
+        default:
+            if (net > 0.0f) acc = net + add;
+            else { float d = ep.t / (ep.t + 1.0f); acc = net * d + add; }
+            break;
+    }
+    return fmax_ref(acc, floor);
+}
+
+__global__ void __launch_bounds__(32)
+mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, EpochArgs ep) {
+    const int x = blockIdx.x, lane = threadIdx.x;
+    if (g.info_player[x] != ep.walker) return;
+    const int A = g.info_actions[x], row = g.info_row[x];
+    const int role = lane / A, a = lane - role * A;  // 0 regret, 1 weight, 2 payoff+visits
+    // regret matching on the PRE-fold regrets (the policy every Decisions of this epoch carries,
+    // strategy/profile.rs:47-51); read by all lanes before any lane stores a folded regret
+    float rd = 0.0f, ra = 0.0f;
+    for (int k = 0; k < A; ++k) {
+        float r = fmax_ref(table[row + k].regret, kEps);
+        rd = rd + r;
+        if (k == a) ra = r;
+    }
+    const float sigma = ra / rd;
+    __syncwarp();
+    if (role > 2) return;
+    const size_t total = (size_t)sc.nblk * sc.cap;
+    const int32_t* off = sc.m_off + (size_t)x * sc.nblk;
+    const int32_t* cnt = sc.m_cnt + (size_t)x * sc.nblk;
+
+    if (role == 0) {  // solver.rs:143-152 update_regret
+        float R = table[row + a].regret;
+        const float* dr = sc.dr + (size_t)a * total;
+        unsigned long long ups = 0;
+        for (int b = 0; b < sc.nblk; ++b) {
+            const int n = cnt[b];
+            const size_t base = (size_t)b * sc.cap + off[b];
+            for (int i = 0; i < n; ++i) {
+                if (sc.mask[base + i] >> a & 1u) { R = regret_gain(ep, R, dr[base + i]); ++ups; }
+            }
+        }
+        table[row + a].regret = R;
+        if (ups) atomicAdd(&sc.counters[2], ups);
+    } else if (role == 1) {  // solver.rs:158-167 update_weight
+        int n = 0;
+        for (int b = 0; b < sc.nblk; ++b) n += cnt[b];
+        float W = table[row + a].weight;
+        float add;
+        switch (ep.weight_sched) {
+            case RBP_WEIGHT_CONSTANT: add = sigma; break;
+            case RBP_WEIGHT_LINEAR: add = sigma * ep.t; break;
+            case RBP_WEIGHT_QUADRATIC: add = sigma * ep.t * ep.t; break;
+            default: add = sigma; break;
+        }
+        if (ep.weight_sched == RBP_WEIGHT_EXPONENTIAL) {
+            for (int i = 0; i < n; ++i) W = fmax_ref(W * 0.9999f + add, kEps);
+        } else {
+            for (int i = 0; i < n; ++i) W = fmax_ref(W + add, kEps);
+        }
+        table[row + a].weight = W;
+    } else {  // solver.rs:174-192 update_payoff (Welford) then update_visits
+        float ev = table[row + a].payoff;
+        uint32_t v = table[row + a].visits;
+        for (int b = 0; b < sc.nblk; ++b) {
+            const int n = cnt[b];
+            const size_t base = (size_t)b * sc.cap + off[b];
+            for (int i = 0; i < n; ++i) {
+                ev += (sc.pay[base + i] - ev) / (float)(v + 1u);
+                v += 1u;
+            }
+        }
+        table[row + a].payoff = ev;
+        table[row + a].visits = v;
+    }
+}
+
+// ───────────────────────────── K4: exploitability ─────────────────────────────
+// solver.rs:327-338 + strategy/nash.rs:31-193 on the enumerated tree.  One block; bottom-up level sweeps
+// replace the reference's recursion (pure function of the subtree ⇒ same f32 results); the upward
+// `external_reach` product keeps the reference's nearest-ancestor-first order.
+__global__ void __launch_bounds__(256)
+mccfr_exploit_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, float* __restrict__ U,
+                     float* __restrict__ cfv, int32_t* __restrict__ br, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_avg = reinterpret_cast<float*>(smem_raw);  // [I][4]
+    const int I = g.n_infos, tid = threadIdx.x, T = blockDim.x;
+    for (int x = tid; x < I; x += T) {  // profile.rs:41-45 averaged_distribution
+        const int A = g.info_actions[x], row = g.info_row[x];
+        float w[kMaxActions], sum = 0.0f;
+        for (int a = 0; a < A; ++a) { w[a] = fmax_ref(table[row + a].weight, kEps); sum = sum + w[a]; }
+        for (int a = 0; a < A; ++a) s_avg[x * kMaxActions + a] = w[a] / sum;
+    }
+    __syncthreads();
+    float total = 0.0f;
+    for (int hero = 0; hero < 2; ++hero) {
+        for (int pass = 0; pass < 2; ++pass) {  // pass 0: average strategy everywhere; pass 1: hero plays br[]
+            for (int d = g.n_levels - 1; d >= 0; --d) {
+                for (int n = g.level_start[d] + tid; n < g.level_start[d + 1]; n += T) {
+                    const FlatNode nd = g.nodes[n];
+                    float u;
+                    if (nd.n_child == 0) {
+                        u = hero == 0 ? nd.payoff0 : g.payoff1[n];
+                    } else if (nd.turn == TURN_CHANCE) {  // nash.rs:116
+                        float s = 0.0f;
+                        for (int k = 0; k < nd.n_child; ++k) s = s + U[nd.first_child + k];
+                        u = s / (float)nd.n_child;
+                    } else if (pass == 1 && nd.turn == hero) {  // nash.rs:118-124
+                        u = U[nd.first_child + br[nd.info]];
+                    } else {  // nash.rs:125-132
+                        float s = 0.0f;
+                        for (int k = 0; k < nd.n_child; ++k) s = s + s_avg[nd.info * kMaxActions + k] * U[nd.first_child + k];
+                        u = s;
+                    }
+                    U[n] = u;
+                }
+                __syncthreads();
+            }
+            if (pass == 1) break;
+            // nash.rs:171-193 optimal_cfactual_choice
+            for (int xa = tid; xa < I * kMaxActions; xa += T) {
+                const int x = xa / kMaxActions, a = xa - x * kMaxActions;
+                if (g.info_player[x] != hero || a >= g.info_actions[x]) continue;
+                float sum = 0.0f;
+                for (int s = g.span_start[x]; s < g.span_start[x + 1]; ++s) {
+                    const int c = g.nodes[g.span_nodes[s]].first_child + a;
+                    float reach = 1.0f;  // nash.rs:140-145 external_reach
+                    for (int node = c; g.parent[node] >= 0; node = g.parent[node]) {
+                        const int par = g.parent[node];
+                        const FlatNode pn = g.nodes[par];
+                        if (pn.turn <= TURN_P1 && pn.turn != hero) reach = reach * s_avg[pn.info * kMaxActions + (node - pn.first_child)];
+                    }
+                    sum = sum + reach * U[c];
+                }
+                cfv[xa] = sum;
+            }
+            __syncthreads();
+            for (int x = tid; x < I; x += T) {
+                if (g.info_player[x] != hero) continue;
+                float best = 0.0f; int besta = -1;
+                for (int a = 0; a < g.info_actions[x]; ++a) {
+                    const float v = cfv[x * kMaxActions + a];
+                    if (besta < 0 || !(v < best)) { best = v; besta = a; }  // Iterator::max_by keeps the last maximum
+                }
+                br[x] = besta;
+            }
+            __syncthreads();
+        }
+        total = total + U[0];
+        __syncthreads();
+    }
+    if (tid == 0) *out = total / 2.0f;
+}
+
+// L2 flush between timed steps (bench hygiene): stream a buffer larger than the 126 MB L2
+__global__ void l2_flush_kernel(uint4* buf, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = make_uint4((uint32_t)i, 0u, 0u, 0u);
+}
+
+// table reset: every row reads as the reference's "missing" row (book.rs:93-122; default_regret = 0 for flat games)
+__global__ void table_reset_kernel(rbp_encounter_t* table, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) table[i] = rbp_encounter_t{0.0f, 0.0f, 0.0f, 0u};
+}
+
+}  // namespace rbp
+
+// ───────────────────────────── host: handle + C ABI ─────────────────────────────
+using namespace rbp;
+
+struct rbp_solver {
+    FlatGame game;
+    DevGame dev{};
+    Scratch sc{};
+    rbp_encounter_t* table = nullptr;
+    float *U = nullptr, *cfv = nullptr, *expl = nullptr;
+    int32_t* br = nullptr;
+    std::vector<void*> owned;
+    std::vector<uint8_t> touched;  // rows written by import (export lists visits>0 or touched)
+    cudaStream_t stream = nullptr;
+    int device = 0, regret = 0, weight = 0, sampling = 0, fold_mode = 0, batch = 1;
+    int world_rank = 0, world_size = 1;
+    uint64_t seed = 0, epochs = 0;
+    rbp_hyper_t hyper{};
+    size_t sample_smem = 0;
+    uint4* flush_buf = nullptr;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+template <class T>
+int upload(rbp_solver* s, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    RBP_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    s->owned.push_back(p);
+    RBP_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return RBP_OK;
+}
+template <class T>
+int alloc(rbp_solver* s, size_t n, T** out) {
+    void* p = nullptr;
+    RBP_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    s->owned.push_back(p);
+    RBP_CUDA(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    *out = static_cast<T*>(p);
+    return RBP_OK;
+}
+EpochArgs epoch_args(const rbp_solver* s) {
+    EpochArgs ep{};
+    ep.seed_lo = (uint32_t)s->seed; ep.seed_hi = (uint32_t)(s->seed >> 32);
+    ep.epoch = (uint32_t)s->epochs;
+    ep.walker = (int)(s->epochs % 2);  // book.rs:142-144
+    ep.batch = s->batch;
+    ep.tree_base = s->world_rank * s->batch;
+    ep.sampling = s->sampling;
+    ep.hyper = s->hyper;
+    ep.regret_sched = s->regret; ep.weight_sched = s->weight;
+    ep.t = (float)s->epochs;
+    ep.disc_pos = powf(ep.t / 1.0f, 1.5f);
+    ep.disc_neg = powf(ep.t / 1.0f, 0.5f);
+    return ep;
+}
+int launch_sample(rbp_solver* s, const EpochArgs& ep) {
+    mccfr_sample_kernel<<<s->sc.nblk, kTreesPerBlock, s->sample_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+int launch_fold(rbp_solver* s, const EpochArgs& ep) {
+    mccfr_fold_kernel<<<s->dev.n_infos, 32, 0, s->stream>>>(s->dev, s->table, s->sc, ep);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* rbp_status_string(int status) {
+    switch (status) {
+        case RBP_OK: return "ok";
+        case RBP_ERR_INVALID: return "invalid argument";
+        case RBP_ERR_NO_DEVICE: return "no CUDA device (librbp_b200 has no CPU fallback)";
+        case RBP_ERR_CUDA: return "CUDA error";
+        case RBP_ERR_CAPACITY: return "capacity exceeded";
+        case RBP_ERR_STATE: return "bad call sequence";
+        default: return "unknown status";
+    }
+}
+const char* rbp_last_error(void) {
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    copy = g_err;
+    return copy.c_str();
+}
+uint64_t rbp_kernel_launches(void) { return g_launches.load(); }
+int rbp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void rbp_hyper_default(rbp_hyper_t* h) {
+    h->temperature = 1.0f; h->smoothing = 2.0f; h->curiosity = 0.05f;
+    h->prune_threshold = -3e5f; h->prune_explore = 0.05f; h->prune_warmup = 16384; h->regret_min = -4e6f;
+}
+void rbp_philox4x32_10(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+    Philox4 p = philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
+    for (int i = 0; i < 4; ++i) out[i] = p.r[i];
+}
+
+int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_mode, int batch, uint64_t seed,
+                      const rbp_hyper_t* hyper, int device, rbp_solver_t** out) {
+    if (!out) return RBP_ERR_INVALID;
+    *out = nullptr;
+    if (regret < 0 || regret > 4 || weight < 0 || weight > 3 || batch < 1) return RBP_ERR_INVALID;
+    if (sampling != RBP_SAMPLING_EXTERNAL && sampling != RBP_SAMPLING_PRUNABLE && sampling != RBP_SAMPLING_PLURIBUS) {
+        set_last_error("training needs a sampling scheme (VanillaSampling is exploitability-only, sample/vanilla.rs)");
+        return RBP_ERR_INVALID;
+    }
+    if (fold_mode != RBP_FOLD_ORDERED) { set_last_error("fold mode not built yet"); return RBP_ERR_INVALID; }
+    if (rbp_device_count() <= device) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
+    rbp_solver* s = new rbp_solver();
+    if (!build_flat_game(game, &s->game)) { delete s; return RBP_ERR_INVALID; }
+    const FlatGame& G = s->game;
+    if (G.max_tree_nodes > kMaxTreeNodes || G.max_tree_infos > kMaxRecords || G.max_depth + 1 > kMaxDepth ||
+        (int)G.info_key.size() > kMaxInfos || (int)G.nodes.size() > 32767) {
+        set_last_error("flat game exceeds compiled capacities");
+        delete s;
+        return RBP_ERR_CAPACITY;
+    }
+    s->device = device; s->regret = regret; s->weight = weight; s->sampling = sampling; s->fold_mode = fold_mode;
+    s->batch = batch; s->seed = seed;
+    if (hyper) s->hyper = *hyper; else rbp_hyper_default(&s->hyper);
+    int st = RBP_OK;
+    auto fail = [&](int code) { rbp_solver_destroy(s); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    DevGame& d = s->dev;
+    if ((st = upload(s, G.nodes, &d.nodes))) return fail(st);
+    if ((st = upload(s, G.payoff1, &d.payoff1))) return fail(st);
+    if ((st = upload(s, G.root_table, &d.root_table))) return fail(st);
+    if ((st = upload(s, G.info_row, &d.info_row))) return fail(st);
+    if ((st = upload(s, G.info_actions, &d.info_actions))) return fail(st);
+    if ((st = upload(s, G.info_player, &d.info_player))) return fail(st);
+    if ((st = upload(s, G.parent, &d.parent))) return fail(st);
+    if ((st = upload(s, G.level_start, &d.level_start))) return fail(st);
+    if ((st = upload(s, G.span_start, &d.span_start))) return fail(st);
+    if ((st = upload(s, G.span_nodes, &d.span_nodes))) return fail(st);
+    d.n_nodes = (int)G.nodes.size(); d.n_infos = (int)G.info_key.size(); d.n_rows = G.n_rows;
+    d.n_levels = (int)G.level_start.size() - 1; d.deck = G.deck;
+    if ((st = alloc(s, (size_t)G.n_rows, &s->table))) return fail(st);
+    s->touched.assign(G.n_rows, 0);
+    Scratch& sc = s->sc;
+    sc.nblk = (batch + kTreesPerBlock - 1) / kTreesPerBlock;
+    sc.cap = kTreesPerBlock * G.max_tree_infos;
+    const size_t total = (size_t)sc.nblk * sc.cap;
+    if ((st = alloc(s, total, &sc.pay))) return fail(st);
+    if ((st = alloc(s, total * kMaxActions, &sc.dr))) return fail(st);
+    if ((st = alloc(s, total, &sc.mask))) return fail(st);
+    if ((st = alloc(s, (size_t)d.n_infos * sc.nblk, &sc.m_off))) return fail(st);
+    if ((st = alloc(s, (size_t)d.n_infos * sc.nblk, &sc.m_cnt))) return fail(st);
+    if ((st = alloc(s, 3, &sc.counters))) return fail(st);
+    if ((st = alloc(s, (size_t)d.n_nodes, &s->U))) return fail(st);
+    if ((st = alloc(s, (size_t)d.n_infos * kMaxActions, &s->cfv))) return fail(st);
+    if ((st = alloc(s, (size_t)d.n_infos, &s->br))) return fail(st);
+    if ((st = alloc(s, 1, &s->expl))) return fail(st);
+    s->sample_smem = (size_t)d.n_infos * (3 * kMaxActions * sizeof(float) + 10 * sizeof(uint32_t));
+    if (cudaFuncSetAttribute(mccfr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sample_smem) != cudaSuccess)
+        return fail(RBP_ERR_CUDA);
+    *out = s;
+    return RBP_OK;
+}
+
+int rbp_solver_set_world(rbp_solver_t* s, int world_rank, int world_size) {
+    if (!s || world_size < 1 || world_rank < 0 || world_rank >= world_size) return RBP_ERR_INVALID;
+    s->world_rank = world_rank; s->world_size = world_size;
+    return RBP_OK;
+}
+
+void rbp_solver_destroy(rbp_solver_t* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    for (void* p : s->owned) cudaFree(p);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    delete s;
+}
+
+int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs) {
+    if (!s) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    for (uint64_t i = 0; i < n_epochs; ++i) {
+        EpochArgs ep = epoch_args(s);
+        int st;
+        if ((st = launch_sample(s, ep))) return st;
+        if ((st = launch_fold(s, ep))) return st;
+        s->epochs += 1;  // book.rs:138-140
+    }
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
+
+int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, float* ms_total, float* ms_sample, float* ms_fold) {
+    if (!s || !ms_total) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    const size_t flush_n = (size_t)192 << 20 >> 4;  // 192 MiB of uint4
+    if (flush_l2 && !s->flush_buf) {
+        int st = alloc(s, flush_n, &s->flush_buf);
+        if (st) return st;
+    }
+    while (s->events.size() < 3 * n_epochs) {
+        cudaEvent_t e;
+        RBP_CUDA(cudaEventCreate(&e));
+        s->events.push_back(e);
+    }
+    for (uint64_t i = 0; i < n_epochs; ++i) {
+        EpochArgs ep = epoch_args(s);
+        int st;
+        if (flush_l2) {
+            l2_flush_kernel<<<148 * 8, 256, 0, s->stream>>>(s->flush_buf, flush_n);
+            RBP_CUDA(cudaGetLastError());
+        }
+        RBP_CUDA(cudaEventRecord(s->events[3 * i], s->stream));
+        if ((st = launch_sample(s, ep))) return st;
+        RBP_CUDA(cudaEventRecord(s->events[3 * i + 1], s->stream));
+        if ((st = launch_fold(s, ep))) return st;
+        RBP_CUDA(cudaEventRecord(s->events[3 * i + 2], s->stream));
+        s->epochs += 1;
+    }
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    double tot = 0, a = 0, b = 0;
+    for (uint64_t i = 0; i < n_epochs; ++i) {
+        float x;
+        RBP_CUDA(cudaEventElapsedTime(&x, s->events[3 * i], s->events[3 * i + 2])); tot += x;
+        RBP_CUDA(cudaEventElapsedTime(&x, s->events[3 * i], s->events[3 * i + 1])); a += x;
+        RBP_CUDA(cudaEventElapsedTime(&x, s->events[3 * i + 1], s->events[3 * i + 2])); b += x;
+    }
+    *ms_total = (float)tot;
+    if (ms_sample) *ms_sample = (float)a;
+    if (ms_fold) *ms_fold = (float)b;
+    return RBP_OK;
+}
+
+int rbp_solver_epochs(rbp_solver_t* s, uint64_t* out) {
+    if (!s || !out) return RBP_ERR_INVALID;
+    *out = s->epochs;
+    return RBP_OK;
+}
+
+int rbp_solver_exploitability(rbp_solver_t* s, float* out) {
+    if (!s || !out) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    size_t smem = (size_t)s->dev.n_infos * kMaxActions * sizeof(float);
+    mccfr_exploit_kernel<<<1, 256, smem, s->stream>>>(s->dev, s->table, s->U, s->cfv, s->br, s->expl);
+    RBP_LAUNCHED();
+    RBP_CUDA(cudaMemcpyAsync(out, s->expl, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
+
+int rbp_solver_counters(rbp_solver_t* s, uint64_t out[3]) {
+    if (!s || !out) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    unsigned long long tmp[3];
+    RBP_CUDA(cudaMemcpyAsync(tmp, s->sc.counters, sizeof tmp, cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 3; ++i) out[i] = tmp[i];
+    return RBP_OK;
+}
+
+int rbp_profile_export(rbp_solver_t* s, rbp_profile_row_t* rows, int cap, int* n_out) {
+    if (!s || !n_out || (cap > 0 && !rows)) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    std::vector<rbp_encounter_t> host(s->game.n_rows);
+    RBP_CUDA(cudaMemcpyAsync(host.data(), s->table, host.size() * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<rbp_profile_row_t> all;
+    for (size_t x = 0; x < s->game.info_key.size(); ++x)
+        for (int a = 0; a < s->game.info_actions[x]; ++a) {
+            int r = s->game.info_row[x] + a;
+            if (host[r].visits > 0 || s->touched[r]) all.push_back(rbp_profile_row_t{s->game.info_key[x], (uint32_t)a, host[r]});
+        }
+    std::sort(all.begin(), all.end(), [](const rbp_profile_row_t& p, const rbp_profile_row_t& q) {
+        return p.info_key != q.info_key ? p.info_key < q.info_key : p.action < q.action;
+    });
+    *n_out = (int)all.size();
+    for (int i = 0; i < (int)all.size() && i < cap; ++i) rows[i] = all[i];
+    return (int)all.size() > cap && cap > 0 ? RBP_ERR_CAPACITY : RBP_OK;
+}
+
+int rbp_profile_import(rbp_solver_t* s, const rbp_profile_row_t* rows, int n, uint64_t epochs) {
+    if (!s || (n > 0 && !rows) || n < 0) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    std::vector<rbp_encounter_t> host(s->game.n_rows, rbp_encounter_t{0.0f, 0.0f, 0.0f, 0u});
+    std::fill(s->touched.begin(), s->touched.end(), 0);
+    for (int i = 0; i < n; ++i) {
+        int x = -1;
+        for (size_t k = 0; k < s->game.info_key.size(); ++k)
+            if (s->game.info_key[k] == rows[i].info_key) { x = (int)k; break; }
+        if (x < 0 || rows[i].action >= s->game.info_actions[x]) { set_last_error("import: unknown (info_key, action)"); return RBP_ERR_INVALID; }
+        int r = s->game.info_row[x] + (int)rows[i].action;
+        host[r] = rows[i].row;
+        s->touched[r] = 1;
+    }
+    RBP_CUDA(cudaMemcpyAsync(s->table, host.data(), host.size() * sizeof(rbp_encounter_t), cudaMemcpyHostToDevice, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    s->epochs = epochs;
+    return RBP_OK;
+}
+
+int rbp_profile_averaged(rbp_solver_t* s, uint32_t info_key, float* probs, int cap, int* n_out) {
+    if (!s || !probs || !n_out) return RBP_ERR_INVALID;
+    int x = -1;
+    for (size_t k = 0; k < s->game.info_key.size(); ++k)
+        if (s->game.info_key[k] == info_key) { x = (int)k; break; }
+    if (x < 0) return RBP_ERR_INVALID;
+    const int A = s->game.info_actions[x];
+    if (cap < A) return RBP_ERR_CAPACITY;
+    RBP_CUDA(cudaSetDevice(s->device));
+    rbp_encounter_t e[kMaxActions];
+    RBP_CUDA(cudaMemcpyAsync(e, s->table + s->game.info_row[x], A * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    float w[kMaxActions], sum = 0.0f;  // profile.rs:41-45 (a read-out of device rows, not a compute path)
+    for (int a = 0; a < A; ++a) { w[a] = e[a].weight > kEps ? e[a].weight : kEps; sum = sum + w[a]; }
+    for (int a = 0; a < A; ++a) probs[a] = w[a] / sum;
+    *n_out = A;
+    return RBP_OK;
+}
+
+int rbp_solver_game_shape(rbp_solver_t* s, int out[6]) {
+    if (!s || !out) return RBP_ERR_INVALID;
+    out[0] = (int)s->game.nodes.size(); out[1] = s->game.n_terminals; out[2] = (int)s->game.info_key.size();
+    out[3] = s->game.n_rows; out[4] = s->game.max_tree_nodes; out[5] = s->game.max_tree_infos;
+    return RBP_OK;
+}
+
+int rbp_solver_sample(rbp_solver_t*) { set_last_error("not built yet"); return RBP_ERR_STATE; }
+int rbp_solver_delta_buffer(rbp_solver_t*, void**, size_t*) { set_last_error("not built yet"); return RBP_ERR_STATE; }
+int rbp_solver_fold_gathered(rbp_solver_t*, const void*, int) { set_last_error("not built yet"); return RBP_ERR_STATE; }
+
+}  // extern "C"

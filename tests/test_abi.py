@@ -1,0 +1,58 @@
+"""The C-ABI library loads on a CPU-only host, exports every symbol include/rbp.h declares, and refuses to compute
+without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            text = open(os.path.join(ROOT, "include", fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            names |= set(re.findall(r"\b(rbp_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_declares_symbols():
+    assert len(declared_symbols()) >= 15
+
+
+def test_every_declared_symbol_is_exported(rbp):
+    l = rbp.load_library()
+    missing = [n for n in declared_symbols() if not hasattr(l, n)]
+    assert not missing, missing
+
+
+def test_philox_contract_matches_random123(rbp):
+    l = rbp.load_library()
+    out = (ctypes.c_uint32 * 4)()
+    l.rbp_philox4x32_10((ctypes.c_uint32 * 4)(0, 0, 0, 0), (ctypes.c_uint32 * 2)(0, 0), out)
+    assert list(out) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_hyper_defaults(rbp):
+    h = rbp.Hyper().c
+    # crates/mccfr/src/hyperparams/{sampling.rs:39-50,pruning.rs:40-55,training.rs:52-60}
+    assert (h.temperature, h.smoothing, round(h.curiosity, 6)) == (1.0, 2.0, 0.05)
+    assert (h.prune_threshold, round(h.prune_explore, 6), h.prune_warmup, h.regret_min) == (-3e5, 0.05, 16384, -4e6)
+
+
+def test_info_key_packing(rbp):
+    assert rbp.kuhn_info("J", "Open") == 1
+    assert rbp.kuhn_info("K", "CheckBet") == 1 | (3 << 1) | (2 << 3)
+    assert rbp.leduc_info("Q", None, "Open", None) == 1 | (1 << 8)
+    assert rbp.leduc_info("K", "J", "Raised", "Checked") == 1 | (1 << 1) | (2 << 3) | (2 << 5) | (2 << 8)
+
+
+def test_no_cpu_fallback(rbp):
+    if rbp.load_library().rbp_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(rbp.RbpError) as e:
+        rbp.Solver("kuhn")
+    assert e.value.status == -2  # RBP_ERR_NO_DEVICE

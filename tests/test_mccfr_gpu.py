@@ -1,0 +1,117 @@
+"""GPU parity: the CUDA MCCFR path (through the C ABI) against the oracle on identical Philox streams.
+
+The bar for this path is bit-exact: every f32 operation of sampling, value computation and the ordered fold is
+performed in the oracle's order without FMA contraction, so tables, exploitability and counters must be identical
+(the north-star's 1e-5 relative / 1e-4 exploitability tolerances are therefore met with margin zero).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rows_equal(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    for f in ("info_key", "action", "visits"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("regret", "weight", "payoff"):
+        x, y = a[f].view(np.uint32), b[f].view(np.uint32)
+        bad = np.nonzero(x != y)[0]
+        assert bad.size == 0, (f, a[bad[:4]], b[bad[:4]])
+
+
+@pytest.mark.parametrize("game", ["kuhn", "leduc"])
+def test_game_shape_and_untrained_exploitability(rbp, oracle, game):
+    g, o = rbp.Solver(game), oracle.OracleSolver(game)
+    st, shape = o.tree_stats(), g.game_shape()
+    assert (shape["nodes"], shape["terminals"], shape["infosets"]) == (st["nodes"], st["terminals"], st["infosets"])
+    assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32)
+
+
+CASES = [
+    # game, regret, weight, sampling, batch, epochs
+    ("kuhn", "FlooredRegret", "LinearWeight", "ExternalSampling", 1, 2000),
+    ("kuhn", "SummedRegret", "ConstantWeight", "ExternalSampling", 7, 300),
+    ("kuhn", "LinearRegret", "QuadraticWeight", "ExternalSampling", 128, 100),
+    ("kuhn", "DiscountedRegret", "ExponentialWeight", "ExternalSampling", 300, 60),
+    ("kuhn", "AsymmetricRegret", "LinearWeight", "PrunableSampling", 64, 100),
+    ("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", 1, 3000),
+    ("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", 1024, 64),
+    ("leduc", "LinearRegret", "LinearWeight", "ExternalSampling", 129, 100),
+    ("leduc", "DiscountedRegret", "LinearWeight", "ExternalSampling", 256, 80),
+    ("leduc", "SummedRegret", "ConstantWeight", "PrunableSampling", 500, 40),
+    ("leduc", "AsymmetricRegret", "QuadraticWeight", "PluribusSampling", 200, 60),
+]
+
+
+@pytest.mark.parametrize("game,regret,weight,sampling,batch,epochs", CASES)
+def test_bit_exact_against_oracle(rbp, oracle, game, regret, weight, sampling, batch, epochs):
+    g = rbp.Solver(game, regret, weight, sampling, batch=batch, seed=11)
+    o = oracle.OracleSolver(game, regret, weight, sampling, batch=batch, seed=11, threads=4)
+    for chunk in (1, 1, epochs - 2):
+        g.step(chunk)
+        o.step(chunk)
+        rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.epochs == o.epochs == epochs
+    assert g.counters() == o.counters()
+    assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32)
+
+
+def test_pluribus_pruning_engages(rbp, oracle):
+    # tiny warm-up and a threshold regrets actually cross, so the pruned branch of sample/pluribus.rs:85-99 runs
+    hyper = rbp.Hyper(prune_warmup=4, prune_threshold=-0.5, prune_explore=0.25)
+    g = rbp.Solver("leduc", "SummedRegret", "LinearWeight", "PluribusSampling", batch=256, seed=5, hyper=hyper)
+    o = oracle.OracleSolver("leduc", "SummedRegret", "LinearWeight", "PluribusSampling", batch=256, seed=5, threads=4)
+    o.set_hyper(prune_warmup=4, prune_threshold=-0.5, prune_explore=0.25)
+    g.step(60)
+    o.step(60)
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.counters() == o.counters()
+
+
+def test_large_batch_full_size(rbp, oracle):
+    # the bench configuration (16384 trees / epoch), a few epochs, still bit-exact
+    g = rbp.Solver("leduc", batch=16384, seed=0)
+    o = oracle.OracleSolver("leduc", batch=16384, seed=0, threads=8)
+    g.step(6)
+    o.step(6)
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.counters() == o.counters()
+
+
+def test_convergence_properties_at_scale(rbp):
+    # size-independent properties at 1M trees: exploitability under the reference's own threshold
+    # (crates/leduc/src/solver.rs:121-123), average strategies are distributions, visits add up
+    g = rbp.Solver("leduc", batch=1024, seed=1).step(1024)
+    assert g.exploitability() < 0.080
+    rows = g.profile_rows()
+    assert len(rows) == 240
+    c = g.counters()
+    assert int(rows["visits"].sum()) == 2 * c["infos"]  # every Decisions bumps both rows of its infoset
+    assert c["updates"] == 2 * c["infos"]
+    for key in np.unique(rows["info_key"]):
+        p = g.averaged_distribution(int(key))
+        assert abs(sum(p) - 1.0) < 1e-6 and min(p) >= 0.0
+
+
+def test_import_export_roundtrip_and_resume(rbp, oracle):
+    a = rbp.Solver("leduc", batch=64, seed=9).step(30)
+    rows, epochs = a.profile_rows().copy(), a.epochs
+    b = rbp.Solver("leduc", batch=64, seed=9)
+    b.import_rows(rows, epochs)
+    rows_equal(b.profile_rows(), rows)
+    a.step(10)
+    b.step(10)
+    rows_equal(a.profile_rows(), b.profile_rows())
+    o = oracle.OracleSolver("leduc", batch=64, seed=9, threads=2)
+    o.import_rows(rows, epochs)
+    o.step(10)
+    rows_equal(a.profile_rows(), o.profile_rows())
+
+
+def test_timed_step_matches_untimed(rbp):
+    a = rbp.Solver("leduc", batch=512, seed=2).step(12)
+    b = rbp.Solver("leduc", batch=512, seed=2)
+    total, s, f = b.step_timed(12, flush_l2=True)
+    assert total > 0 and s > 0 and f > 0 and abs(total - (s + f)) < 0.25 * total
+    rows_equal(a.profile_rows(), b.profile_rows())
