@@ -96,6 +96,9 @@ int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs);
  * events, optionally preceded by an (untimed) L2 flush; returns the summed device milliseconds of the n steps and,
  * if non-NULL, the summed durations of the sampling and fold kernels. */
 int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, float* ms_total, float* ms_sample, float* ms_fold);
+/* device self-test: the fold kernel's reciprocal-based Welford division (payoff += (x - payoff)/(visits+1),
+ * solver.rs:174-181) against IEEE division for every count in [1, max_count] x `samples` dividends */
+int rbp_selftest_div_by_count(uint32_t max_count, uint32_t samples, uint64_t* mismatches);
 /* `RefProf::t` (crates/mccfr/src/strategy/profile.rs:14) */
 int rbp_solver_epochs(rbp_solver_t* s, uint64_t* out);
 /* `Solver::exploitability` (solver.rs:327-338 → crates/mccfr/src/strategy/nash.rs:31-193) */
@@ -121,6 +124,24 @@ int rbp_solver_game_shape(rbp_solver_t* s, int out[6]);
 int rbp_solver_sample(rbp_solver_t* s);                                   /* K1 only (+ local blocked sums)     */
 int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes); /* this rank's partial sums (device) */
 int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size); /* K2 over all ranks  */
+
+/* ─────────────────────────────── deuce: hand strength and river equity ─────────────────────────────── */
+
+/* `Strength::from(Hand)` (crates/deuce/src/strength.rs:19-31 → evaluator.rs:39-177) for a batch of 52-bit hands
+ * (bit = 4*rank + suit, crates/deuce/src/{hand.rs,card.rs}; 5 to 7 cards).  Packed so that unsigned integer order
+ * equals the reference's derived `Ord` on (Ranking, Kickers) (ranking.rs:33-44, default build: FullHouse < Flush):
+ *   bits 24-27 tag {HighCard 0, OnePair 1, TwoPair 2, ThreeOAK 3, Straight 4, FullHouse 5, Flush 6, FourOAK 7,
+ *   StraightFlush 8} | 20-23 first rank | 16-19 second rank | 0-12 `Kickers` rank bits (kicks.rs:4).          */
+int rbp_eval_batch(const uint64_t* hands, int64_t n, uint32_t* strength_out);
+/* `Observation::equity` (crates/deuce/src/observation.rs:45-62) for n river observations (pocket: 2 cards, public:
+ * 5 cards): wins/(wins+losses) over all C(45,2)=990 villain holes, ties dropped, 0.5 if nothing decisive; bucket =
+ * `Abstraction::from(equity)` index = round(100 p) (crates/kicker/src/abstraction.rs:43-45,61-63).  Any output
+ * pointer may be NULL.  This is the per-isomorphism work of `Lookup::grow(Street::Rive)` (lloyd/src/lookup.rs:177-184). */
+int rbp_river_equity_batch(const uint64_t* pocket, const uint64_t* pub, int64_t n, float* equity_out, uint8_t* bucket_out,
+                           uint32_t* wins_out, uint32_t* total_out);
+/* same, on device buffers and a caller stream (cudaStream_t passed as void*) — no copies, asynchronous */
+int rbp_river_equity_device(const uint64_t* d_pocket, const uint64_t* d_public, int64_t n, float* d_equity, uint8_t* d_bucket,
+                            uint32_t* d_wins, uint32_t* d_total, void* stream);
 
 #ifdef __cplusplus
 }

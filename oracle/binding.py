@@ -107,3 +107,30 @@ class OracleSolver:
         out = (ctypes.c_float * 8)()
         n = lib().orc_solver_averaged(self._h, info_key, out)
         return [out[i] for i in range(n)]
+
+
+def _deuce():
+    l = lib()
+    if not getattr(l, "_deuce_ready", False):
+        vp, i64 = ctypes.c_void_p, ctypes.c_int64
+        l.orc_eval_batch.argtypes = [vp, i64, vp]
+        l.orc_river_equity_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, ctypes.c_int]
+        l._deuce_ready = True
+    return l
+
+
+def eval_batch(hands):
+    hands = np.ascontiguousarray(hands, dtype=np.uint64)
+    out = np.zeros(len(hands), dtype=np.uint32)
+    _deuce().orc_eval_batch(hands.ctypes.data, len(hands), out.ctypes.data)
+    return out
+
+
+def river_equity_batch(pocket, public, threads=8):
+    pocket = np.ascontiguousarray(pocket, dtype=np.uint64)
+    public = np.ascontiguousarray(public, dtype=np.uint64)
+    n = len(pocket)
+    eq, bk = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    w, t = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    _deuce().orc_river_equity_batch(pocket.ctypes.data, public.ctypes.data, n, eq.ctypes.data, bk.ctypes.data, w.ctypes.data, t.ctypes.data, threads)
+    return eq, bk, w, t

@@ -55,6 +55,7 @@ def load_library():
     l.rbp_solver_destroy.restype = None
     l.rbp_solver_step.argtypes = [vp, u64]
     l.rbp_solver_step_timed.argtypes = [vp, u64, i32, P(ctypes.c_float), P(ctypes.c_float), P(ctypes.c_float)]
+    l.rbp_selftest_div_by_count.argtypes = [u32, u32, P(u64)]
     l.rbp_solver_epochs.argtypes = [vp, P(u64)]
     l.rbp_solver_exploitability.argtypes = [vp, P(ctypes.c_float)]
     l.rbp_solver_counters.argtypes = [vp, P(u64)]
@@ -65,6 +66,10 @@ def load_library():
     l.rbp_solver_sample.argtypes = [vp]
     l.rbp_solver_delta_buffer.argtypes = [vp, P(vp), P(ctypes.c_size_t)]
     l.rbp_solver_fold_gathered.argtypes = [vp, vp, i32]
+    i64 = ctypes.c_int64
+    l.rbp_eval_batch.argtypes = [vp, i64, vp]
+    l.rbp_river_equity_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    l.rbp_river_equity_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     _lib = l
     return l
 

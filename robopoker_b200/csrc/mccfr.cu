@@ -95,7 +95,6 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
     uint32_t* s_woff = s_bits + 4 * I;                          // [4][I] warp offsets
     uint32_t* s_cnt = s_woff + 4 * I;                           // [I]
     uint32_t* s_off = s_cnt + I;                                // [I]
-    __shared__ uint32_t s_scan[kTreesPerBlock / 32 + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -311,7 +310,6 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
             if (x < I) s_off[x] = carry + inc - v;
             carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
-        if (lane == 0) s_scan[0] = carry;
     }
     __syncthreads();
     const size_t total = (size_t)sc.nblk * sc.cap;
@@ -342,34 +340,58 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
 }
 
 // ───────────────────────────── K3: ordered fold ─────────────────────────────
-__device__ __forceinline__ float regret_gain(const EpochArgs& ep, float net, float add) {
-    float acc, floor = ep.hyper.regret_min;
-    switch (ep.regret_sched) {
-        case RBP_REGRET_SUMMED: acc = net + add; floor = -INFINITY; break;
-        case RBP_REGRET_FLOORED: acc = net + add; floor = 0.0f; break;
-        case RBP_REGRET_LINEAR: { float d = ep.t / (ep.t + 1.0f); acc = net * d + add; break; }
-        case RBP_REGRET_DISCOUNTED: {
-            float x = net > 0.0f ? ep.disc_pos : (net < 0.0f ? ep.disc_neg : ep.t);
-            float d = x / (x + 1.0f);
-            acc = net * d + add;
-            break;
-        }
-        default:
-            if (net > 0.0f) acc = net + add;
-            else { float d = ep.t / (ep.t + 1.0f); acc = net * d + add; }
-            break;
-    }
-    return fmax_ref(acc, floor);
+// One block (3 warps) per walker infoset.  warp 0 folds regrets, warp 1 weights, warp 2 payoff+visits — the three
+// chains of solver.rs:143-192 are independent, so they run concurrently; inside a warp lane `a` owns row `a`.
+// Each chain is inherently serial (one schedule application per Decisions, in tree order), so the kernel is built
+// around chain latency: the infoset's records are staged 32 tree-blocks at a time into shared memory with
+// coalesced loads, and the chain loop then runs on shared-memory operands only.
+constexpr int kFoldChunkBlocks = 32;
+constexpr int kFoldCap = kFoldChunkBlocks * kTreesPerBlock;  // records staged per chunk (one per tree at most)
+
+struct RegretConst {  // loop-invariant parts of regret/*.rs
+    float d_lin, d_pos, d_neg, d_zero, floor;
+};
+template <int RS>
+__device__ __forceinline__ float regret_gain(const RegretConst& c, float net, float add) {
+    float acc;
+    if (RS == RBP_REGRET_SUMMED || RS == RBP_REGRET_FLOORED) acc = net + add;
+    else if (RS == RBP_REGRET_LINEAR) acc = net * c.d_lin + add;
+    else if (RS == RBP_REGRET_DISCOUNTED) acc = net * (net > 0.0f ? c.d_pos : (net < 0.0f ? c.d_neg : c.d_zero)) + add;
+    else acc = net > 0.0f ? net + add : net * c.d_lin + add;
+    return fmax_ref(acc, c.floor);
 }
 
-__global__ void __launch_bounds__(32)
+// a / b for b = (float)(visits + 1), with the reciprocal prepared off the dependent chain.
+// rb = RN(1/b); q = RN(a*rb); r = a - b*q (exact, FMA); q' = RN(q + r*rb) is the correctly rounded quotient
+// (Markstein's theorem) whenever no intermediate under/overflows and b's significand is not all ones — both
+// guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
+__device__ __forceinline__ float div_by_count(float a, float b, float rb) {
+    const float aa = fabsf(a);
+    const bool safe = aa > 1.0e-18f && aa < 1.0e18f && (__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu;
+    if (!safe) return a / b;
+    const float q = a * rb;
+    const float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, rb, q);
+}
+
+template <int RS, int WS, bool MASKED>
+__global__ void __launch_bounds__(96)
 mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, EpochArgs ep) {
-    const int x = blockIdx.x, lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int x = blockIdx.x;
     if (g.info_player[x] != ep.walker) return;
     const int A = g.info_actions[x], row = g.info_row[x];
-    const int role = lane / A, a = lane - role * A;  // 0 regret, 1 weight, 2 payoff+visits
-    // regret matching on the PRE-fold regrets (the policy every Decisions of this epoch carries,
-    // strategy/profile.rs:47-51); read by all lanes before any lane stores a folded regret
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_dr = reinterpret_cast<float*>(smem_raw);          // [A][kFoldCap]  (warp 0)
+    float* s_pay = s_dr + (size_t)A * kFoldCap;                // [kFoldCap]     (warp 2)
+    uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_pay + kFoldCap);  // [kFoldCap] (warp 0)
+    const size_t total = (size_t)sc.nblk * sc.cap;
+    const int32_t* off = sc.m_off + (size_t)x * sc.nblk;
+    const int32_t* cnt = sc.m_cnt + (size_t)x * sc.nblk;
+
+    // regret matching on the PRE-fold regrets: the policy every Decisions of this epoch carries
+    // (strategy/profile.rs:47-51); all warps read before warp 0 stores
+    const int a = lane < A ? lane : 0;
     float rd = 0.0f, ra = 0.0f;
     for (int k = 0; k < A; ++k) {
         float r = fmax_ref(table[row + k].regret, kEps);
@@ -377,56 +399,118 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
         if (k == a) ra = r;
     }
     const float sigma = ra / rd;
-    __syncwarp();
-    if (role > 2) return;
-    const size_t total = (size_t)sc.nblk * sc.cap;
-    const int32_t* off = sc.m_off + (size_t)x * sc.nblk;
-    const int32_t* cnt = sc.m_cnt + (size_t)x * sc.nblk;
+    __syncthreads();
 
-    if (role == 0) {  // solver.rs:143-152 update_regret
-        float R = table[row + a].regret;
-        const float* dr = sc.dr + (size_t)a * total;
-        unsigned long long ups = 0;
-        for (int b = 0; b < sc.nblk; ++b) {
-            const int n = cnt[b];
-            const size_t base = (size_t)b * sc.cap + off[b];
-            for (int i = 0; i < n; ++i) {
-                if (sc.mask[base + i] >> a & 1u) { R = regret_gain(ep, R, dr[base + i]); ++ups; }
-            }
-        }
-        table[row + a].regret = R;
-        if (ups) atomicAdd(&sc.counters[2], ups);
-    } else if (role == 1) {  // solver.rs:158-167 update_weight
+    if (warp == 1) {  // solver.rs:158-167 update_weight: n identical applications
         int n = 0;
-        for (int b = 0; b < sc.nblk; ++b) n += cnt[b];
-        float W = table[row + a].weight;
-        float add;
-        switch (ep.weight_sched) {
-            case RBP_WEIGHT_CONSTANT: add = sigma; break;
-            case RBP_WEIGHT_LINEAR: add = sigma * ep.t; break;
-            case RBP_WEIGHT_QUADRATIC: add = sigma * ep.t * ep.t; break;
-            default: add = sigma; break;
+        for (int b = lane; b < sc.nblk; b += 32) n += cnt[b];
+        for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
+        if (lane < A) {
+            float W = table[row + lane].weight;
+            float add = sigma;
+            if (WS == RBP_WEIGHT_LINEAR) add = sigma * ep.t;
+            if (WS == RBP_WEIGHT_QUADRATIC) add = sigma * ep.t * ep.t;
+            if (WS == RBP_WEIGHT_EXPONENTIAL) {
+                for (int i = 0; i < n; ++i) W = fmax_ref(W * 0.9999f + add, kEps);
+            } else {
+#pragma unroll 8
+                for (int i = 0; i < n; ++i) W = fmax_ref(W + add, kEps);
+            }
+            table[row + lane].weight = W;
         }
-        if (ep.weight_sched == RBP_WEIGHT_EXPONENTIAL) {
-            for (int i = 0; i < n; ++i) W = fmax_ref(W * 0.9999f + add, kEps);
-        } else {
-            for (int i = 0; i < n; ++i) W = fmax_ref(W + add, kEps);
+        return;
+    }
+
+    RegretConst rc;
+    rc.d_lin = ep.t / (ep.t + 1.0f);
+    rc.d_pos = ep.disc_pos / (ep.disc_pos + 1.0f);
+    rc.d_neg = ep.disc_neg / (ep.disc_neg + 1.0f);
+    rc.d_zero = rc.d_lin;
+    rc.floor = RS == RBP_REGRET_SUMMED ? -INFINITY : (RS == RBP_REGRET_FLOORED ? 0.0f : ep.hyper.regret_min);
+
+    float R = 0.0f, ev = 0.0f;
+    uint32_t visits = 0;
+    unsigned long long ups = 0;
+    if (lane < A) {
+        R = table[row + lane].regret;
+        ev = table[row + lane].payoff;
+        visits = table[row + lane].visits;
+    }
+    for (int c = 0; c < sc.nblk; c += kFoldChunkBlocks) {
+        const int b = c + lane;
+        const int n_mine = b < sc.nblk ? cnt[b] : 0;
+        const int o_mine = b < sc.nblk ? off[b] : 0;
+        int incl = n_mine;
+        for (int d = 1; d < 32; d <<= 1) {
+            int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += up;
         }
-        table[row + a].weight = W;
-    } else {  // solver.rs:174-192 update_payoff (Welford) then update_visits
-        float ev = table[row + a].payoff;
-        uint32_t v = table[row + a].visits;
-        for (int b = 0; b < sc.nblk; ++b) {
-            const int n = cnt[b];
-            const size_t base = (size_t)b * sc.cap + off[b];
-            for (int i = 0; i < n; ++i) {
-                ev += (sc.pay[base + i] - ev) / (float)(v + 1u);
-                v += 1u;
+        const int chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const int p_mine = incl - n_mine;
+        // stage the chunk: segment s = this infoset's records of tree-block c+s, contiguous and in tree order
+        for (int sgm = 0; sgm < kFoldChunkBlocks; ++sgm) {
+            const int ns = __shfl_sync(0xFFFFFFFFu, n_mine, sgm);
+            const int os = __shfl_sync(0xFFFFFFFFu, o_mine, sgm);
+            const int ps = __shfl_sync(0xFFFFFFFFu, p_mine, sgm);
+            const size_t base = (size_t)(c + sgm) * sc.cap + os;
+            for (int i = lane; i < ns; i += 32) {
+                if (warp == 0) {
+                    for (int k = 0; k < A; ++k) s_dr[k * kFoldCap + ps + i] = sc.dr[(size_t)k * total + base + i];
+                    if (MASKED) s_mask[ps + i] = sc.mask[base + i];
+                } else {
+                    s_pay[ps + i] = sc.pay[base + i];
+                }
             }
         }
-        table[row + a].payoff = ev;
-        table[row + a].visits = v;
+        __syncwarp();
+        if (lane < A) {
+            if (warp == 0) {  // solver.rs:143-152 update_regret
+                const float* d = s_dr + lane * kFoldCap;
+#pragma unroll 8
+                for (int e = 0; e < chunk_total; ++e) {
+                    if (!MASKED || (s_mask[e] >> lane & 1u)) { R = regret_gain<RS>(rc, R, d[e]); ++ups; }
+                }
+            } else {  // solver.rs:174-192 update_payoff (Welford) then update_visits
+#pragma unroll 4
+                for (int e = 0; e < chunk_total; ++e) {
+                    const float bcount = (float)(visits + 1u);
+                    const float rb = __frcp_rn(bcount);
+                    ev += div_by_count(s_pay[e] - ev, bcount, rb);
+                    visits += 1u;
+                }
+            }
+        }
+        __syncwarp();
     }
+    if (lane < A) {
+        if (warp == 0) {
+            table[row + lane].regret = R;
+            if (ups) atomicAdd(&sc.counters[2], ups);
+        } else {
+            table[row + lane].payoff = ev;
+            table[row + lane].visits = visits;
+        }
+    }
+}
+
+// self-test of div_by_count against IEEE division: every count b in [1, max_count] against `samples` dividends
+// (Philox bits reinterpreted so that all exponents in the guarded range, both signs, occur)
+__global__ void div_selftest_kernel(uint32_t max_count, uint32_t samples, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1; b <= max_count; b += gridDim.x * blockDim.x) {
+        const float fb = (float)b, rb = __frcp_rn(fb);
+        for (uint32_t k = 0; k < samples; k += 4) {
+            Philox4 p = philox4x32_10(b, k, 0x5e1f7e57u, 0u, 0x1234u, 0x5678u);
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bits = p.r[j];
+                uint32_t expo = 64u + ((bits >> 23) & 0xFFu) % 128u;  // 2^-63 .. 2^64
+                float a = __uint_as_float((bits & 0x807FFFFFu) | (expo << 23));
+                if ((k + j) % 16 == 0) a = (float)((int)(bits % 2001u) - 1000) * 0.25f;  // small payoffs like Leduc's
+                if (__float_as_uint(div_by_count(a, fb, rb)) != __float_as_uint(a / fb)) ++bad;
+            }
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // ───────────────────────────── K4: exploitability ─────────────────────────────
@@ -537,7 +621,7 @@ struct rbp_solver {
     int world_rank = 0, world_size = 1;
     uint64_t seed = 0, epochs = 0;
     rbp_hyper_t hyper{};
-    size_t sample_smem = 0;
+    size_t sample_smem = 0, fold_smem = 0;
     uint4* flush_buf = nullptr;
     std::vector<cudaEvent_t> events;
 };
@@ -581,10 +665,53 @@ int launch_sample(rbp_solver* s, const EpochArgs& ep) {
     RBP_LAUNCHED();
     return RBP_OK;
 }
-int launch_fold(rbp_solver* s, const EpochArgs& ep) {
-    mccfr_fold_kernel<<<s->dev.n_infos, 32, 0, s->stream>>>(s->dev, s->table, s->sc, ep);
+template <int RS, int WS>
+int launch_fold_rw(rbp_solver* s, const EpochArgs& ep) {
+    const bool masked = s->sampling != RBP_SAMPLING_EXTERNAL;
+    if (masked) mccfr_fold_kernel<RS, WS, true><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
+    else mccfr_fold_kernel<RS, WS, false><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
     RBP_LAUNCHED();
     return RBP_OK;
+}
+template <int RS>
+int launch_fold_r(rbp_solver* s, const EpochArgs& ep) {
+    switch (s->weight) {
+        case RBP_WEIGHT_CONSTANT: return launch_fold_rw<RS, RBP_WEIGHT_CONSTANT>(s, ep);
+        case RBP_WEIGHT_LINEAR: return launch_fold_rw<RS, RBP_WEIGHT_LINEAR>(s, ep);
+        case RBP_WEIGHT_QUADRATIC: return launch_fold_rw<RS, RBP_WEIGHT_QUADRATIC>(s, ep);
+        default: return launch_fold_rw<RS, RBP_WEIGHT_EXPONENTIAL>(s, ep);
+    }
+}
+int launch_fold(rbp_solver* s, const EpochArgs& ep) {
+    switch (s->regret) {
+        case RBP_REGRET_SUMMED: return launch_fold_r<RBP_REGRET_SUMMED>(s, ep);
+        case RBP_REGRET_FLOORED: return launch_fold_r<RBP_REGRET_FLOORED>(s, ep);
+        case RBP_REGRET_LINEAR: return launch_fold_r<RBP_REGRET_LINEAR>(s, ep);
+        case RBP_REGRET_DISCOUNTED: return launch_fold_r<RBP_REGRET_DISCOUNTED>(s, ep);
+        default: return launch_fold_r<RBP_REGRET_ASYMMETRIC>(s, ep);
+    }
+}
+template <int RS, int WS>
+int fold_attr_rw(size_t smem) {
+    RBP_CUDA(cudaFuncSetAttribute(mccfr_fold_kernel<RS, WS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RBP_CUDA(cudaFuncSetAttribute(mccfr_fold_kernel<RS, WS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return RBP_OK;
+}
+template <int RS>
+int fold_attr_r(size_t smem) {
+    int st;
+    if ((st = fold_attr_rw<RS, RBP_WEIGHT_CONSTANT>(smem))) return st;
+    if ((st = fold_attr_rw<RS, RBP_WEIGHT_LINEAR>(smem))) return st;
+    if ((st = fold_attr_rw<RS, RBP_WEIGHT_QUADRATIC>(smem))) return st;
+    return fold_attr_rw<RS, RBP_WEIGHT_EXPONENTIAL>(smem);
+}
+int fold_attr(size_t smem) {
+    int st;
+    if ((st = fold_attr_r<RBP_REGRET_SUMMED>(smem))) return st;
+    if ((st = fold_attr_r<RBP_REGRET_FLOORED>(smem))) return st;
+    if ((st = fold_attr_r<RBP_REGRET_LINEAR>(smem))) return st;
+    if ((st = fold_attr_r<RBP_REGRET_DISCOUNTED>(smem))) return st;
+    return fold_attr_r<RBP_REGRET_ASYMMETRIC>(smem);
 }
 }  // namespace
 
@@ -681,6 +808,10 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
     s->sample_smem = (size_t)d.n_infos * (3 * kMaxActions * sizeof(float) + 10 * sizeof(uint32_t));
     if (cudaFuncSetAttribute(mccfr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sample_smem) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
+    int max_a = 1;
+    for (uint8_t na : G.info_actions) max_a = std::max<int>(max_a, na);
+    s->fold_smem = (size_t)kFoldCap * ((max_a + 1) * sizeof(float) + 1);
+    if ((st = fold_attr(s->fold_smem))) return fail(st);
     *out = s;
     return RBP_OK;
 }
@@ -752,6 +883,21 @@ int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, floa
     *ms_total = (float)tot;
     if (ms_sample) *ms_sample = (float)a;
     if (ms_fold) *ms_fold = (float)b;
+    return RBP_OK;
+}
+
+int rbp_selftest_div_by_count(uint32_t max_count, uint32_t samples, uint64_t* mismatches) {
+    if (!mismatches) return RBP_ERR_INVALID;
+    if (rbp_device_count() < 1) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
+    unsigned long long* d = nullptr;
+    RBP_CUDA(cudaMalloc(&d, sizeof *d));
+    RBP_CUDA(cudaMemset(d, 0, sizeof *d));
+    div_selftest_kernel<<<148 * 8, 256>>>(max_count, samples, d);
+    RBP_LAUNCHED();
+    unsigned long long h = 0;
+    RBP_CUDA(cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost));
+    RBP_CUDA(cudaFree(d));
+    *mismatches = h;
     return RBP_OK;
 }
 

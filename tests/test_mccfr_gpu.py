@@ -115,3 +115,12 @@ def test_timed_step_matches_untimed(rbp):
     total, s, f = b.step_timed(12, flush_l2=True)
     assert total > 0 and s > 0 and f > 0 and abs(total - (s + f)) < 0.25 * total
     rows_equal(a.profile_rows(), b.profile_rows())
+
+
+def test_welford_division_is_ieee_exact(rbp):
+    # the fold kernel divides by (visits+1) through a precomputed reciprocal + two FMAs; it must equal IEEE `/`
+    import ctypes
+
+    bad = ctypes.c_uint64(1)
+    st = rbp.load_library().rbp_selftest_div_by_count(1 << 22, 64, ctypes.byref(bad))
+    assert st == 0 and bad.value == 0, bad.value
