@@ -143,6 +143,50 @@ int rbp_river_equity_batch(const uint64_t* pocket, const uint64_t* pub, int64_t 
 int rbp_river_equity_device(const uint64_t* d_pocket, const uint64_t* d_public, int64_t n, float* d_equity, uint8_t* d_bucket,
                             uint32_t* d_wins, uint32_t* d_total, void* stream);
 
+/* ─────────────────────────────── lloyd / elkan: k-means abstraction layers ─────────────────────────────── */
+
+/* distance kinds of `Metric::emd` (crates/lloyd/src/metric.rs:109-115) */
+enum { RBP_KMEANS_W1 = 0 /* Equity::variation over the 101 river-equity buckets (turn layer) */ };
+
+typedef struct rbp_kmeans rbp_kmeans_t;
+
+/* `Layer::<K,N>::build` (crates/lloyd/src/layer.rs:250-272): N points = dense histograms `counts[n][bins]` (u8 counts;
+ * the reference's `Bins{weight, counts:[usize;N]}`, lloyd/src/bins.rs:29-38 — weight = Σ counts), K clusters.
+ * The points are copied to the device once and stay resident. */
+int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out);
+void rbp_kmeans_destroy(rbp_kmeans_t* h);
+/* `Layer::init_centroids` k-means++ (layer.rs:140-181).  The reference's SmallRng/WeightedIndex<f32> stream is
+ * replaced by the integer-weight contract: round r draws word = Philox(counter=(r,0,0,3), key=seed),
+ * q_i = (u64)(min(potential_i, 2^20) * 2^32), T = Σ q_i, x = mulhi64(word, T), pick = first i with x < Σ_{k<=i} q_k.
+ * chosen_out[k] (nullable) receives the chosen point indices. */
+int rbp_kmeans_init_pp(rbp_kmeans_t* h, uint64_t seed, int32_t* chosen_out);
+/* explicit centroids: `counts[k][bins]` (u64 sums of member counts, as `Absorb` produces them, elkan/src/absorb.rs:16-21) */
+int rbp_kmeans_set_centroids(rbp_kmeans_t* h, const uint64_t* counts);
+/* `Elkan::init_bounds` (crates/elkan/src/elkan.rs:39-47): argmin_j distance(c_j, x) with first-minimum ties */
+int rbp_kmeans_init_bounds(rbp_kmeans_t* h);
+/* `Elkan::step_elkan` (elkan.rs:153-168) + `Prior::tally` (elkan/src/prior.rs:35-47): drift_out[k], sizes_out[k],
+ * *reassigned_out are nullable */
+int rbp_kmeans_step(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out);
+/* the same step split at the one exchange point for point-sharded multi-GPU runs: after _local each rank holds
+ * integer partial sums (K x (bins+1) u64: counts + weight) plus sizes[k]/reassigned u32 counters on the device —
+ * all-reduce(sum) them in place (integer: order-independent, bit-identical on every rank), then call _finish. */
+int rbp_kmeans_step_local(rbp_kmeans_t* h);
+int rbp_kmeans_accumulator(rbp_kmeans_t* h, void** dev_ptr, size_t* bytes);
+int rbp_kmeans_counters(rbp_kmeans_t* h, void** dev_sizes /* u32[k] */, void** dev_reassigned /* u32[1] */);
+void* rbp_kmeans_stream(rbp_kmeans_t* h); /* cudaStream_t the kernels run on */
+int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out);
+/* `Layer::lookup` (layer.rs:44-60): fresh naive argmin against the current centroids; dist_out nullable */
+int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* assign_out, float* dist_out);
+/* `Layer::future` payload: centroid histograms (counts[k][bins], weights[k]); either may be NULL */
+int rbp_kmeans_centroids(rbp_kmeans_t* h, uint64_t* counts_out, uint64_t* weights_out);
+/* `Layer::metric` (layer.rs:85-101) + `Metric::from` normalisation (metric.rs:127-141): tri_out[k(k-1)/2] in the
+ * triangular order of `Pair::merge` (lloyd/src/pair.rs:36-39): index(i>j) = i(i-1)/2 + j */
+int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out);
+/* `Bounds<K>` state per point (elkan/src/bounds.rs:19-28) for inspection: assign[n], upper[n], lower[n][k], stale[n] */
+int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out);
+/* CUDA-event timing on the library stream: what = 0 full step, 1 N x K assignment sweep */
+int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,3 +134,89 @@ def river_equity_batch(pocket, public, threads=8):
     w, t = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
     _deuce().orc_river_equity_batch(pocket.ctypes.data, public.ctypes.data, n, eq.ctypes.data, bk.ctypes.data, w.ctypes.data, t.ctypes.data, threads)
     return eq, bk, w, t
+
+
+class OracleKmeans:
+    """oracle/lloyd.hpp: Elkan k-means over W1 histograms (turn layer)."""
+
+    def __init__(self, counts, k, threads=8):
+        counts = np.ascontiguousarray(counts, dtype=np.uint8)
+        self.n, self.bins = counts.shape
+        self.k = k
+        l = lib()
+        if not getattr(l, "_lloyd_ready", False):
+            vp, i32 = ctypes.c_void_p, ctypes.c_int
+            l.orc_kmeans_create.restype = vp
+            l.orc_kmeans_create.argtypes = [vp, i32, i32, i32, i32]
+            l.orc_kmeans_destroy.argtypes = [vp]
+            l.orc_kmeans_init_pp.argtypes = [vp, ctypes.c_uint64, vp]
+            l.orc_kmeans_set_centroids_from_points.argtypes = [vp, vp]
+            l.orc_kmeans_init_bounds.argtypes = [vp]
+            l.orc_kmeans_step.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_uint32)]
+            l.orc_kmeans_state.argtypes = [vp, vp, vp, vp, vp]
+            l.orc_kmeans_centroids.argtypes = [vp, vp, vp]
+            l.orc_kmeans_assign.argtypes = [vp, vp, vp]
+            l.orc_kmeans_metric.argtypes = [vp, vp]
+            l.orc_variation.restype = ctypes.c_float
+            l.orc_variation.argtypes = [vp, vp, i32]
+            l.orc_kmeans_dist_evals.restype = ctypes.c_uint64
+            l.orc_kmeans_dist_evals.argtypes = [vp]
+            l._lloyd_ready = True
+        self._l = l
+        self._h = l.orc_kmeans_create(counts.ctypes.data, self.n, self.bins, k, threads)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.orc_kmeans_destroy(self._h)
+            self._h = None
+
+    def init_centroids(self, seed=0):
+        chosen = np.zeros(self.k, np.int32)
+        self._l.orc_kmeans_init_pp(self._h, seed, chosen.ctypes.data)
+        return chosen
+
+    def set_centroids_from_points(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._l.orc_kmeans_set_centroids_from_points(self._h, idx.ctypes.data)
+
+    def init_bounds(self):
+        self._l.orc_kmeans_init_bounds(self._h)
+
+    def step(self):
+        drift, sizes, re = np.zeros(self.k, np.float32), np.zeros(self.k, np.uint32), ctypes.c_uint32()
+        self._l.orc_kmeans_step(self._h, drift.ctypes.data, sizes.ctypes.data, ctypes.byref(re))
+        return drift, sizes, re.value
+
+    def bounds(self, with_lower=False):
+        a, u, st = np.zeros(self.n, np.uint32), np.zeros(self.n, np.float32), np.zeros(self.n, np.uint8)
+        lo = np.zeros((self.n, self.k), np.float32) if with_lower else None
+        self._l.orc_kmeans_state(self._h, a.ctypes.data, u.ctypes.data, lo.ctypes.data if with_lower else None, st.ctypes.data)
+        return a, u, lo, st
+
+    def future(self):
+        c, w = np.zeros((self.k, self.bins), np.uint64), np.zeros(self.k, np.uint64)
+        self._l.orc_kmeans_centroids(self._h, c.ctypes.data, w.ctypes.data)
+        return c, w
+
+    def lookup(self, with_distance=False):
+        out, d = np.zeros(self.n, np.uint32), np.zeros(self.n, np.float32)
+        self._l.orc_kmeans_assign(self._h, out.ctypes.data, d.ctypes.data)
+        return (out, d) if with_distance else out
+
+    def metric(self):
+        tri = np.zeros(self.k * (self.k - 1) // 2, np.float32)
+        self._l.orc_kmeans_metric(self._h, tri.ctypes.data)
+        return tri
+
+    def dist_evals(self):
+        return self._l.orc_kmeans_dist_evals(self._h)
+
+
+def variation(x, y):
+    x = np.ascontiguousarray(x, dtype=np.uint32)
+    y = np.ascontiguousarray(y, dtype=np.uint32)
+    OracleKmeans  # ensure argtypes are set lazily through a constructed instance elsewhere
+    l = lib()
+    l.orc_variation.restype = ctypes.c_float
+    l.orc_variation.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    return l.orc_variation(x.ctypes.data, y.ctypes.data, len(x))

@@ -9,6 +9,7 @@ There is no CPU fallback: every compute call raises `RbpError` without a CUDA de
 """
 from ._ffi import RbpError, lib, load_library  # noqa: F401
 from . import deuce  # noqa: F401
+from . import lloyd  # noqa: F401
 from .solver import (  # noqa: F401
     FOLD_BATCHED, FOLD_ORDERED, GAMES, REGRETS, SAMPLERS, WEIGHTS, Hyper, Solver, kuhn_info, leduc_info,
 )

@@ -70,6 +70,25 @@ def load_library():
     l.rbp_eval_batch.argtypes = [vp, i64, vp]
     l.rbp_river_equity_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     l.rbp_river_equity_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    f32p = P(ctypes.c_float)
+    l.rbp_kmeans_create.argtypes = [i32, i64, i32, i32, vp, i32, P(vp)]
+    l.rbp_kmeans_destroy.argtypes = [vp]
+    l.rbp_kmeans_destroy.restype = None
+    l.rbp_kmeans_init_pp.argtypes = [vp, u64, vp]
+    l.rbp_kmeans_set_centroids.argtypes = [vp, vp]
+    l.rbp_kmeans_init_bounds.argtypes = [vp]
+    l.rbp_kmeans_step.argtypes = [vp, vp, vp, P(u32)]
+    l.rbp_kmeans_step_local.argtypes = [vp]
+    l.rbp_kmeans_step_finish.argtypes = [vp, vp, vp, P(u32)]
+    l.rbp_kmeans_accumulator.argtypes = [vp, P(vp), P(ctypes.c_size_t)]
+    l.rbp_kmeans_counters.argtypes = [vp, P(vp), P(vp)]
+    l.rbp_kmeans_stream.argtypes = [vp]
+    l.rbp_kmeans_stream.restype = vp
+    l.rbp_kmeans_assign.argtypes = [vp, vp, vp]
+    l.rbp_kmeans_centroids.argtypes = [vp, vp, vp]
+    l.rbp_kmeans_metric.argtypes = [vp, vp]
+    l.rbp_kmeans_bounds.argtypes = [vp, vp, vp, vp, vp]
+    l.rbp_kmeans_timed.argtypes = [vp, i32, i32, f32p]
     _lib = l
     return l
 

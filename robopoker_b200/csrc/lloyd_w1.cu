@@ -1,0 +1,785 @@
+// lloyd_w1.cu — the TURN abstraction layer on sm_100a: Elkan/Lloyd k-means over histograms of river-equity
+// buckets under the 1-D Wasserstein distance `Equity::variation`, and its C ABI (include/rbp.h).
+//
+// Reference seams (paths relative to krukah/robopoker):
+//   crates/lloyd/src/layer.rs:136-181,195-248   Layer::{distance, init_centroids (k-means++), cluster}
+//   crates/elkan/src/elkan.rs:39-168            init_bounds, neighbor, pairwises, midpoints, refresh, rebound,
+//                                               recompute, drift, step_elkan;  bounds.rs:57-91 Bounds
+//   crates/lloyd/src/equity.rs:41-53            variation(x, y) = Σ_b |cdf_x(b) − cdf_y(b)| / 101
+//   crates/lloyd/src/bins.rs:58-60,75-82        density = count/weight (f32), merge = integer add
+//   crates/lloyd/src/layer.rs:44-101            lookup (fresh naive argmin), metric (symmetrised, normalised)
+//
+// Design (B200-first, not a port).  `variation` separates: each histogram's f32 CDF is built once (sequential
+// adds, exactly as the reference accumulates it) and a distance is then 101 |a−b| terms summed in bin order.
+// A thread owns one point and keeps its 101-entry CDF in REGISTERS; centroid CDFs sit in shared memory (K ≤ 512
+// per tile, 104-float rows read as broadcast LDS.128) — so a distance is 26 LDS + 202 FADD and the kernels are
+// FP32-pipe bound, while the Elkan bounds (N×K f32, K-major so a warp's accesses coalesce) stream through HBM
+// exactly once per iteration: the previous iteration's drift update (`Bounds::update`) is applied lazily when the
+// bound is next read, fusing the reference's second N×K pass into the first.
+// Elkan's pruning tests are evaluated per point exactly as the reference does (same f32 comparisons, same order,
+// including the mid-loop switch of the pairwise row when a point is reassigned), so assignments, centroids and
+// drifts are bit-identical to the oracle; the distance itself is only computed when some lane of the warp needs it.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rbp {
+
+constexpr int kBins = 101;       // KMEANS_EQTY_CLUSTER_COUNT, crates/pokerkit/src/lib.rs:191
+constexpr int kRow = 112;        // bytes per stored point row (101 counts + pad, 7 x 16 B)
+constexpr int kCdfRow = 104;     // floats per centroid CDF row in shared memory (26 x LDS.128)
+constexpr int kTileK = 512;      // centroids per shared-memory tile (512 x 104 x 4 B = 208 KB)
+constexpr int kThreads = 128;
+
+struct KmDev {
+    const uint8_t* pts;   // [N][kRow]
+    int64_t n;
+    int k;
+    float* cdf;           // [K][kCdfRow] centroid CDFs (current)
+    float* pair;          // [K][kp], kp = K rounded up to 4
+    int kp;
+    float* mid;           // [K]
+    float* drift;         // [K] drift of the PREVIOUS step, applied lazily
+    float* lower;         // [K][N]
+    float* upper;         // [N]
+    uint32_t* assign;     // [N]
+    uint8_t* stale;       // [N]
+    unsigned long long* acc;   // [K][kBins + 1] new centroid counts + weight (integer merge)
+    unsigned long long* ccount;  // [K][kBins + 1] current centroid counts + weight
+    uint32_t* sizes;      // [K]
+    uint32_t* reassigned; // [1]
+    int pending;          // 1 if `drift` has not yet been folded into lower/upper
+};
+
+// ── per-thread point CDF in registers (bins.rs:58-60 density, equity.rs:45-47 running cdf) ──
+__device__ __forceinline__ void load_point_cdf(const uint8_t* __restrict__ row, float (&X)[kBins]) {
+    uint32_t w[kRow / 4];
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int q = 0; q < kRow / 16; ++q) {
+        uint4 v = r4[q];
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+    uint32_t weight = 0;
+#pragma unroll
+    for (int b = 0; b < kBins; ++b) weight += (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+    const float wf = (float)weight;
+    float c = 0.0f;
+#pragma unroll
+    for (int b = 0; b < kBins; ++b) {
+        const uint32_t cnt = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+        c += (float)cnt / wf;   // adding 0/w = +0 leaves c unchanged, as in the reference
+        X[b] = c;
+    }
+}
+
+// distance of the register CDF to up to 4 centroid CDF rows in shared memory (equity.rs:48-52: sequential sum, / 101)
+template <int G>
+__device__ __forceinline__ void dist_group(const float (&X)[kBins], const float* __restrict__ rows, float (&out)[G]) {
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kCdfRow / 4; ++q) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float4 c = *reinterpret_cast<const float4*>(rows + g * kCdfRow + 4 * q);
+            if (4 * q + 0 < kBins) acc[g] += fabsf(X[4 * q + 0 < kBins ? 4 * q + 0 : 0] - c.x);
+            if (4 * q + 1 < kBins) acc[g] += fabsf(X[4 * q + 1 < kBins ? 4 * q + 1 : 0] - c.y);
+            if (4 * q + 2 < kBins) acc[g] += fabsf(X[4 * q + 2 < kBins ? 4 * q + 2 : 0] - c.z);
+            if (4 * q + 3 < kBins) acc[g] += fabsf(X[4 * q + 3 < kBins ? 4 * q + 3 : 0] - c.w);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) out[g] = acc[g] / (float)kBins;
+}
+
+__device__ __forceinline__ void stage_cdf_tile(float* s_cdf, const float* __restrict__ cdf, int j0, int kt) {
+    const float4* src = reinterpret_cast<const float4*>(cdf + (size_t)j0 * kCdfRow);
+    float4* dst = reinterpret_cast<float4*>(s_cdf);
+    for (int t = threadIdx.x; t < kt * (kCdfRow / 4); t += blockDim.x) dst[t] = src[t];
+}
+
+// ── centroid CDFs from integer counts (K threads) ──
+__global__ void centroid_cdf_kernel(const unsigned long long* __restrict__ counts, int k, float* __restrict__ cdf) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const unsigned long long* c = counts + (size_t)j * (kBins + 1);
+    const float wf = (float)c[kBins];
+    float run = 0.0f;
+    for (int b = 0; b < kBins; ++b) {
+        run += (float)c[b] / wf;
+        cdf[(size_t)j * kCdfRow + b] = run;
+    }
+    for (int b = kBins; b < kCdfRow; ++b) cdf[(size_t)j * kCdfRow + b] = 0.0f;
+}
+__device__ __forceinline__ float cdf_distance(const float* __restrict__ a, const float* __restrict__ b) {
+    float acc = 0.0f;
+    for (int q = 0; q < kBins; ++q) acc += fabsf(a[q] - b[q]);
+    return acc / (float)kBins;
+}
+// elkan.rs:80-105 pairwises + midpoints (one block per row i)
+__global__ void pairwise_kernel(const float* __restrict__ cdf, int k, int kp, float* __restrict__ pair, float* __restrict__ mid) {
+    const int i = blockIdx.x;
+    __shared__ float s_min[256];
+    float m = 3.402823466e+38f;  // f32::MAX
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const float d = i == j ? 0.0f : cdf_distance(cdf + (size_t)i * kCdfRow, cdf + (size_t)j * kCdfRow);
+        pair[(size_t)i * kp + j] = d;
+        if (j != i) { const float h = d * 0.5f; m = h < m ? h : m; }  // f32::min ignores a NaN operand
+    }
+    s_min[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { const float o = s_min[threadIdx.x + s]; if (o < s_min[threadIdx.x]) s_min[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mid[i] = s_min[0];
+}
+// elkan.rs:107-109 drift_j = distance(new_j, old_j)
+__global__ void drift_kernel(const float* __restrict__ new_cdf, const float* __restrict__ old_cdf, int k, float* __restrict__ drift) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) drift[j] = cdf_distance(new_cdf + (size_t)j * kCdfRow, old_cdf + (size_t)j * kCdfRow);
+}
+// layer.rs:85-101 metric: (d(i,j) + d(j,i)) / 2 for i > j, triangular index pair.rs:36-39
+__global__ void metric_kernel(const float* __restrict__ cdf, int k, float* __restrict__ tri) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = k * (k - 1) / 2;
+    if (t >= total) return;
+    int hi = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)t)) * 0.5f);
+    while (hi * (hi - 1) / 2 > t) --hi;
+    while ((hi + 1) * hi / 2 <= t) ++hi;
+    const int lo = t - hi * (hi - 1) / 2;
+    const float a = cdf_distance(cdf + (size_t)hi * kCdfRow, cdf + (size_t)lo * kCdfRow);
+    const float b = cdf_distance(cdf + (size_t)lo * kCdfRow, cdf + (size_t)hi * kCdfRow);
+    tri[t] = (a + b) / 2.0f;
+}
+__global__ void metric_normalize_kernel(float* tri, int total) {  // metric.rs:127-141
+    __shared__ float s_max[256];
+    float m = 1.17549435e-38f;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) m = tri[t] > m ? tri[t] : m;
+    s_max[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s && s_max[threadIdx.x + s] > s_max[threadIdx.x]) s_max[threadIdx.x] = s_max[threadIdx.x + s];
+        __syncthreads();
+    }
+    const float mx = s_max[0];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) tri[t] = tri[t] / mx;
+}
+
+// ── naive argmin over all centroids: init_bounds (elkan.rs:39-47), lookup (layer.rs:44-60) ──
+template <bool INIT_BOUNDS>
+__global__ void __launch_bounds__(kThreads)
+assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist) {
+    extern __shared__ __align__(16) float s_cdf[];
+    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    const bool live = i < km.n;
+    float X[kBins];
+    if (live) load_point_cdf(km.pts + (size_t)i * kRow, X);
+    else {
+#pragma unroll
+        for (int b = 0; b < kBins; ++b) X[b] = 0.0f;
+    }
+    float best = 0.0f;
+    int bestj = -1;
+    for (int j0 = 0; j0 < km.k; j0 += kTileK) {
+        const int kt = min(kTileK, km.k - j0);
+        __syncthreads();
+        stage_cdf_tile(s_cdf, km.cdf, j0, kt);
+        __syncthreads();
+        int j = 0;
+        for (; j + 4 <= kt; j += 4) {
+            float d[4];
+            dist_group<4>(X, s_cdf + (size_t)j * kCdfRow, d);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (bestj < 0 || d[g] < best) { best = d[g]; bestj = j0 + j + g; }  // first minimum (Iterator::min_by)
+        }
+        for (; j < kt; ++j) {
+            float d[1];
+            dist_group<1>(X, s_cdf + (size_t)j * kCdfRow, d);
+            if (bestj < 0 || d[0] < best) { best = d[0]; bestj = j0 + j; }
+        }
+    }
+    if (!live) return;
+    if (INIT_BOUNDS) {  // Bounds::from((j, upper)): lower = 0, stale = false (bounds.rs:108-117)
+        km.assign[i] = (uint32_t)bestj;
+        km.upper[i] = best;
+        km.stale[i] = 0;
+        for (int j = 0; j < km.k; ++j) km.lower[(size_t)j * km.n + i] = 0.0f;
+    } else {
+        out_assign[i] = (uint32_t)bestj;
+        if (out_dist) out_dist[i] = best;
+    }
+}
+
+// ── one Elkan step, point side (elkan.rs:153-164 up to recompute) ──
+__global__ void __launch_bounds__(kThreads)
+elkan_step_kernel(KmDev km) {
+    extern __shared__ __align__(16) float s_cdf[];
+    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    const bool live = i < km.n;
+    float X[kBins];
+    if (live) load_point_cdf(km.pts + (size_t)i * kRow, X);
+    else {
+#pragma unroll
+        for (int b = 0; b < kBins; ++b) X[b] = 0.0f;
+    }
+    uint32_t c = 0, c_prior = 0;
+    float u = 0.0f;
+    bool stale = false;
+    if (live) {
+        c = c_prior = km.assign[i];
+        u = km.upper[i];
+        stale = km.stale[i] != 0;
+        if (km.pending) { u += km.drift[c]; stale = true; }  // Bounds::update of the previous step (bounds.rs:65-74)
+    }
+    const bool act = live && u > km.mid[c];  // step_elkan filter: b.u() > midpoints[b.j()]
+    // refresh (elkan.rs:113-117, bounds.rs:76-80): recompute the stale upper bound exactly; lower[c] is written below
+    bool refreshed = false;
+    float refreshed_d = 0.0f;
+    {
+        const bool need = act && stale;
+        if (__any_sync(0xFFFFFFFFu, need)) {
+            if (need) {
+                float d[1];
+                dist_group<1>(X, km.cdf + (size_t)c * kCdfRow, d);  // global/L2 read of one row
+                u = d[0]; stale = false; refreshed = true; refreshed_d = d[0];
+            }
+        }
+    }
+    const uint32_t c_refresh = c;
+    for (int j0 = 0; j0 < km.k; j0 += kTileK) {
+        const int kt = min(kTileK, km.k - j0);
+        __syncthreads();
+        stage_cdf_tile(s_cdf, km.cdf, j0, kt);
+        __syncthreads();
+        for (int jj = 0; jj < kt; jj += 4) {
+            const int g_n = min(4, kt - jj);
+            float l[4], half[4];
+            bool want = false;
+            uint32_t c_row = c;
+            {   // 0.5 * pairwise[c][j..j+3]: one 16-byte gather per group (rows are padded to a multiple of 4)
+                const float4 pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
+                half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                l[g] = 0.0f;
+                if (g < g_n && live) {
+                    const int j = j0 + jj + g;
+                    float v = km.lower[(size_t)j * km.n + i];
+                    if (km.pending) { v = v - km.drift[j]; v = v > 0.0f ? v : 0.0f; }  // (lower - movement).max(0.0)
+                    if (refreshed && (uint32_t)j == c_refresh) v = refreshed_d;        // Bounds::refresh sets lower[j]
+                    l[g] = v;
+                    // could this centroid be examined under the current (c, u)?  (re-tested exactly below)
+                    want |= act && (uint32_t)j != c && u > v && u > half[g];
+                }
+            }
+            // A reassignment inside the group can enable a later member, but only after an earlier member was
+            // examined — so if no member passes under the current state, none is examined at all; otherwise all
+            // four distances are produced together.
+            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (__any_sync(0xFFFFFFFFu, want)) {
+                if (g_n == 4) dist_group<4>(X, s_cdf + (size_t)jj * kCdfRow, d);
+                else
+                    for (int g = 0; g < g_n; ++g) { float t[1]; dist_group<1>(X, s_cdf + (size_t)(jj + g) * kCdfRow, t); d[g] = t[0]; }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g < g_n && live) {
+                    const int j = j0 + jj + g;
+                    if (c != c_row) {  // the pairwise row switches when the point is reassigned mid-loop
+                        const float4 pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
+                        half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
+                        c_row = c;
+                    }
+                    if (want && act && (uint32_t)j != c && u > l[g] && u > half[g]) {  // bounds.rs:57-61 has_shifted
+                        l[g] = d[g];                                   // witness (bounds.rs:81-87)
+                        if (d[g] < u) { c = (uint32_t)j; u = d[g]; }
+                    }
+                    km.lower[(size_t)j * km.n + i] = l[g];
+                }
+            }
+        }
+    }
+    if (live) {
+        km.assign[i] = c;
+        km.upper[i] = u;
+        km.stale[i] = stale ? 1 : 0;
+        if (c != c_prior) atomicAdd(km.reassigned, 1u);
+    }
+}
+
+// ── recompute (elkan.rs:125-142): integer merge of member points into the new centroids ──
+// Each block privatises the K x 102 (bins + weight) u32 accumulators in shared memory over a contiguous slice of
+// points, then flushes non-zero cells with 64-bit global atomics: integer addition, so any order is exact.
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+accumulate_kernel(KmDev km, int64_t per_block) {
+    extern __shared__ __align__(16) unsigned int s_acc[];
+    const int cells = km.k * (kBins + 1);
+    if (SMEM) {
+        for (int t = threadIdx.x; t < cells; t += blockDim.x) s_acc[t] = 0u;
+        __syncthreads();
+    }
+    const int64_t lo = blockIdx.x * per_block, hi = min(km.n, lo + per_block);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint32_t c = km.assign[i];
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(km.pts + (size_t)i * kRow);
+        uint32_t w = 0;
+        for (int q = 0; q < kRow / 4; ++q) {
+            const uint32_t v = row[q];
+            if (!v) continue;
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t cnt = (v >> (8 * t)) & 0xFFu;
+                const int b = 4 * q + t;
+                if (cnt && b < kBins) {
+                    if (SMEM) atomicAdd(&s_acc[c * (kBins + 1) + b], cnt);
+                    else atomicAdd(km.acc + (size_t)c * (kBins + 1) + b, (unsigned long long)cnt);
+                    w += cnt;
+                }
+            }
+        }
+        if (SMEM) atomicAdd(&s_acc[c * (kBins + 1) + kBins], w);
+        else atomicAdd(km.acc + (size_t)c * (kBins + 1) + kBins, (unsigned long long)w);
+        atomicAdd(km.sizes + c, 1u);
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < cells; t += blockDim.x)
+            if (s_acc[t]) atomicAdd(km.acc + t, (unsigned long long)s_acc[t]);
+    }
+}
+
+// ── k-means++ (layer.rs:160-180) under the integer-weight contract of include/rbp.h ──
+__device__ __forceinline__ unsigned long long quantize_potential(float p) {
+    const float q = p < 1048576.0f ? p : 1048576.0f;
+    return (unsigned long long)((double)q * 4294967296.0);
+}
+// potentials update against the newly chosen point + per-block integer sums for the next draw
+__global__ void __launch_bounds__(kThreads)
+pp_update_kernel(KmDev km, float* __restrict__ pot, const int64_t* __restrict__ pick, int first, unsigned long long* __restrict__ bsum) {
+    __shared__ float s_row[kCdfRow];
+    __shared__ unsigned long long s_sum[kThreads / 32];
+    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    const bool live = i < km.n;
+    float p = 1.0f;
+    if (!first) {
+        const int64_t pk = *pick;
+        if (threadIdx.x < 32) {  // CDF of the chosen point, once per block
+            if (threadIdx.x == 0) {
+                float Xp[kBins];
+                load_point_cdf(km.pts + (size_t)pk * kRow, Xp);
+#pragma unroll
+                for (int b = 0; b < kBins; ++b) s_row[b] = Xp[b];
+                for (int b = kBins; b < kCdfRow; ++b) s_row[b] = 0.0f;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            float X[kBins];
+            load_point_cdf(km.pts + (size_t)i * kRow, X);
+            float d[1];
+            dist_group<1>(X, s_row, d);  // distance(&x, h): |a-b| is symmetric, so argument order is immaterial
+            const float d2 = d[0] * d[0];
+            p = pot[i];
+            p = d2 < p ? d2 : p;         // Energy::min(d0, d1)
+            if (i == pk) p = 0.0f;       // potentials[i] = 0 precedes the min and 0 survives it
+            pot[i] = p;
+        }
+    } else if (live) {
+        pot[i] = 1.0f;
+    }
+    unsigned long long q = live ? quantize_potential(p) : 0ull;
+    for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, d);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s_sum[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+// draw: x = mulhi64(word, T); pick = first i with x < Σ_{k<=i} q_k   (one block)
+__global__ void __launch_bounds__(1024)
+pp_pick_kernel(KmDev km, const float* __restrict__ pot, const unsigned long long* __restrict__ bsum, int nb, uint32_t w0, uint32_t w1,
+               int64_t* __restrict__ pick, int round, int32_t* __restrict__ chosen) {
+    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_x, s_base;
+    __shared__ int s_blk;
+    __shared__ bool s_zero;
+    const int tid = threadIdx.x;
+    // each thread owns a contiguous range of blocks
+    const int per = (nb + 1023) / 1024;
+    const int lo = min(nb, tid * per), hi = min(nb, lo + per);
+    unsigned long long mine = 0;
+    for (int b = lo; b < hi; ++b) mine += bsum[b];
+    s_part[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long T = 0;
+        for (int t = 0; t < 1024; ++t) T += s_part[t];
+        const unsigned long long word = (unsigned long long)w0 << 32 | w1;
+        const unsigned long long x = __umul64hi(word, T);
+        s_x = x;
+        s_zero = T == 0ull;
+        unsigned long long cum = 0;
+        int owner = 1023;
+        for (int t = 0; t < 1024; ++t) { if (x < cum + s_part[t]) { owner = t; break; } cum += s_part[t]; }
+        // inside the owner's block range
+        const int olo = min(nb, owner * per), ohi = min(nb, olo + per);
+        int blk = ohi - 1;
+        for (int b = olo; b < ohi; ++b) { if (x < cum + bsum[b]) { blk = b; break; } cum += bsum[b]; }
+        s_blk = blk < 0 ? 0 : blk;
+        s_base = cum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int64_t start = (int64_t)s_blk * kThreads;
+        const int64_t end = min(km.n, start + kThreads);
+        unsigned long long cum = s_base;
+        int64_t p = end - 1;
+        for (int64_t i = start; i < end; ++i) {
+            cum += quantize_potential(pot[i]);
+            if (s_x < cum) { p = i; break; }
+        }
+        if (s_zero) p = km.n - 1;
+        *pick = p;
+        chosen[round] = (int32_t)p;
+    }
+}
+// centroid j := point `pick` (counts + weight)
+__global__ void set_centroid_kernel(KmDev km, const int64_t* __restrict__ pick, int j) {
+    const int b = threadIdx.x;
+    const uint8_t* row = km.pts + (size_t)(*pick) * kRow;
+    __shared__ unsigned int s_w;
+    if (b == 0) s_w = 0;
+    __syncthreads();
+    if (b < kBins) {
+        km.ccount[(size_t)j * (kBins + 1) + b] = row[b];
+        atomicAdd(&s_w, (unsigned int)row[b]);
+    }
+    __syncthreads();
+    if (b == 0) km.ccount[(size_t)j * (kBins + 1) + kBins] = s_w;
+}
+// fold a still-pending drift into the stored bounds (only for state export / tests)
+__global__ void materialize_kernel(KmDev km) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= km.n) return;
+    for (int j = 0; j < km.k; ++j) {
+        float v = km.lower[(size_t)j * km.n + i] - km.drift[j];
+        km.lower[(size_t)j * km.n + i] = v > 0.0f ? v : 0.0f;
+    }
+    km.upper[i] += km.drift[km.assign[i]];
+    km.stale[i] = 1;
+}
+
+}  // namespace rbp
+
+using namespace rbp;
+
+struct rbp_kmeans {
+    KmDev d{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> owned;
+    float* new_cdf = nullptr;
+    float* pot = nullptr;
+    unsigned long long* bsum = nullptr;
+    int64_t* pick = nullptr;
+    int32_t* chosen = nullptr;
+    float* tri = nullptr;
+    uint32_t* tmp_assign = nullptr;
+    float* tmp_dist = nullptr;
+    int nb = 0;
+    size_t smem = 0;
+    bool have_centroids = false, have_bounds = false;
+    uint64_t dist_evals = 0;
+};
+
+namespace {
+template <class T>
+int kalloc(rbp_kmeans* h, size_t n, T** out) {
+    void* p = nullptr;
+    RBP_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    h->owned.push_back(p);
+    RBP_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    *out = static_cast<T*>(p);
+    return RBP_OK;
+}
+int refresh_centroid_tables(rbp_kmeans* h) {  // CDFs of the current centroids
+    centroid_cdf_kernel<<<(h->d.k + 127) / 128, 128, 0, h->stream>>>(h->d.ccount, h->d.k, h->d.cdf);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out) {
+    if (!out) return RBP_ERR_INVALID;
+    *out = nullptr;
+    if (kind != RBP_KMEANS_W1 || bins != kBins || n < 1 || k < 1 || k > n || !counts) {
+        set_last_error("rbp_kmeans_create: only the W1 (Equity::variation, 101 bins) layer is built");
+        return RBP_ERR_INVALID;
+    }
+    if (rbp_device_count() <= device) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
+    rbp_kmeans* h = new rbp_kmeans();
+    h->device = device;
+    auto fail = [&](int code) { rbp_kmeans_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    KmDev& d = h->d;
+    d.n = n; d.k = k;
+    int st;
+    uint8_t* pts = nullptr;
+    if ((st = kalloc(h, (size_t)n * kRow, &pts))) return fail(st);
+    if (cudaMemcpy2DAsync(pts, kRow, counts, bins, bins, n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    d.pts = pts;
+    if ((st = kalloc(h, (size_t)k * kCdfRow, &d.cdf))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * kCdfRow, &h->new_cdf))) return fail(st);
+    d.kp = (k + 3) & ~3;
+    if ((st = kalloc(h, (size_t)k * d.kp + 4, &d.pair))) return fail(st);
+    if ((st = kalloc(h, (size_t)k, &d.mid))) return fail(st);
+    if ((st = kalloc(h, (size_t)k, &d.drift))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * n, &d.lower))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &d.upper))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &d.assign))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &d.stale))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * (kBins + 1), &d.acc))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * (kBins + 1), &d.ccount))) return fail(st);
+    if ((st = kalloc(h, (size_t)k, &d.sizes))) return fail(st);
+    if ((st = kalloc(h, 1, &d.reassigned))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &h->pot))) return fail(st);
+    h->nb = (int)((n + kThreads - 1) / kThreads);
+    if ((st = kalloc(h, (size_t)h->nb, &h->bsum))) return fail(st);
+    if ((st = kalloc(h, 1, &h->pick))) return fail(st);
+    if ((st = kalloc(h, (size_t)k, &h->chosen))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * (k - 1) / 2 + 1, &h->tri))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &h->tmp_assign))) return fail(st);
+    if ((st = kalloc(h, (size_t)n, &h->tmp_dist))) return fail(st);
+    h->smem = (size_t)std::min(k, kTileK) * kCdfRow * sizeof(float);
+    if (cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return fail(RBP_ERR_CUDA);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    *out = h;
+    return RBP_OK;
+}
+
+void rbp_kmeans_destroy(rbp_kmeans_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+}
+
+int rbp_kmeans_init_pp(rbp_kmeans_t* h, uint64_t seed, int32_t* chosen_out) {
+    if (!h) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    for (int r = 0; r < h->d.k; ++r) {
+        pp_update_kernel<<<h->nb, kThreads, 0, h->stream>>>(h->d, h->pot, h->pick, r == 0, h->bsum);
+        RBP_LAUNCHED();
+        Philox4 w = philox4x32_10((uint32_t)r, 0u, 0u, TAG_KMEANSPP, (uint32_t)seed, (uint32_t)(seed >> 32));
+        pp_pick_kernel<<<1, 1024, 0, h->stream>>>(h->d, h->pot, h->bsum, h->nb, w.r[0], w.r[1], h->pick, r, h->chosen);
+        RBP_LAUNCHED();
+        set_centroid_kernel<<<1, 128, 0, h->stream>>>(h->d, h->pick, r);
+        RBP_LAUNCHED();
+    }
+    h->dist_evals += (uint64_t)h->d.n * (h->d.k - 1);
+    int st = refresh_centroid_tables(h);
+    if (st) return st;
+    if (chosen_out) RBP_CUDA(cudaMemcpyAsync(chosen_out, h->chosen, h->d.k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_centroids = true;
+    return RBP_OK;
+}
+
+int rbp_kmeans_set_centroids(rbp_kmeans_t* h, const uint64_t* counts) {
+    if (!h || !counts) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    std::vector<unsigned long long> host((size_t)h->d.k * (kBins + 1));
+    for (int j = 0; j < h->d.k; ++j) {
+        unsigned long long w = 0;
+        for (int b = 0; b < kBins; ++b) { host[(size_t)j * (kBins + 1) + b] = counts[(size_t)j * kBins + b]; w += counts[(size_t)j * kBins + b]; }
+        host[(size_t)j * (kBins + 1) + kBins] = w;
+    }
+    RBP_CUDA(cudaMemcpyAsync(h->d.ccount, host.data(), host.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    int st = refresh_centroid_tables(h);
+    if (st) return st;
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_centroids = true;
+    return RBP_OK;
+}
+
+int rbp_kmeans_init_bounds(rbp_kmeans_t* h) {
+    if (!h) return RBP_ERR_INVALID;
+    if (!h->have_centroids) { set_last_error("init_bounds before centroids"); return RBP_ERR_STATE; }
+    RBP_CUDA(cudaSetDevice(h->device));
+    assign_kernel<true><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
+    RBP_LAUNCHED();
+    h->d.pending = 0;
+    h->dist_evals += (uint64_t)h->d.n * h->d.k;
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_bounds = true;
+    return RBP_OK;
+}
+
+// point side of a step + local integer accumulation; multi-GPU hosts all-reduce the accumulator in between
+int rbp_kmeans_step_local(rbp_kmeans_t* h) {
+    if (!h) return RBP_ERR_INVALID;
+    if (!h->have_bounds) { set_last_error("step before init_bounds"); return RBP_ERR_STATE; }
+    RBP_CUDA(cudaSetDevice(h->device));
+    KmDev& d = h->d;
+    pairwise_kernel<<<d.k, 256, 0, h->stream>>>(d.cdf, d.k, d.kp, d.pair, d.mid);
+    RBP_LAUNCHED();
+    RBP_CUDA(cudaMemsetAsync(d.reassigned, 0, sizeof(uint32_t), h->stream));
+    RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
+    RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
+    elkan_step_kernel<<<h->nb, kThreads, h->smem, h->stream>>>(d);
+    RBP_LAUNCHED();
+    {
+        const size_t acc_smem = (size_t)d.k * (kBins + 1) * sizeof(unsigned int);
+        const int blocks = 148 * 2;
+        const int64_t per_block = (d.n + blocks - 1) / blocks;
+        if (acc_smem <= 200 * 1024) accumulate_kernel<true><<<blocks, 256, acc_smem, h->stream>>>(d, per_block);
+        else accumulate_kernel<false><<<blocks, 256, 0, h->stream>>>(d, per_block);
+        RBP_LAUNCHED();
+    }
+    return RBP_OK;
+}
+int rbp_kmeans_accumulator(rbp_kmeans_t* h, void** dev_ptr, size_t* bytes) {
+    if (!h || !dev_ptr || !bytes) return RBP_ERR_INVALID;
+    *dev_ptr = h->d.acc;
+    *bytes = (size_t)h->d.k * (kBins + 1) * sizeof(unsigned long long);
+    return RBP_OK;
+}
+int rbp_kmeans_counters(rbp_kmeans_t* h, void** dev_sizes, void** dev_reassigned) {
+    if (!h) return RBP_ERR_INVALID;
+    if (dev_sizes) *dev_sizes = h->d.sizes;
+    if (dev_reassigned) *dev_reassigned = h->d.reassigned;
+    return RBP_OK;
+}
+void* rbp_kmeans_stream(rbp_kmeans_t* h) { return h ? (void*)h->stream : nullptr; }
+
+int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
+    if (!h) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    KmDev& d = h->d;
+    centroid_cdf_kernel<<<(d.k + 127) / 128, 128, 0, h->stream>>>(d.acc, d.k, h->new_cdf);
+    RBP_LAUNCHED();
+    drift_kernel<<<(d.k + 127) / 128, 128, 0, h->stream>>>(h->new_cdf, d.cdf, d.k, d.drift);
+    RBP_LAUNCHED();
+    std::swap(d.cdf, h->new_cdf);
+    std::swap(d.acc, d.ccount);
+    d.pending = 1;
+    if (drift_out) RBP_CUDA(cudaMemcpyAsync(drift_out, d.drift, d.k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (sizes_out) RBP_CUDA(cudaMemcpyAsync(sizes_out, d.sizes, d.k * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reassigned_out) RBP_CUDA(cudaMemcpyAsync(reassigned_out, d.reassigned, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return RBP_OK;
+}
+
+int rbp_kmeans_step(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
+    int st = rbp_kmeans_step_local(h);
+    if (st) return st;
+    return rbp_kmeans_step_finish(h, drift_out, sizes_out, reassigned_out);
+}
+
+int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* assign_out, float* dist_out) {
+    if (!h || !assign_out) return RBP_ERR_INVALID;
+    if (!h->have_centroids) { set_last_error("assign before centroids"); return RBP_ERR_STATE; }
+    RBP_CUDA(cudaSetDevice(h->device));
+    assign_kernel<false><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+    RBP_LAUNCHED();
+    h->dist_evals += (uint64_t)h->d.n * h->d.k;
+    RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (dist_out) RBP_CUDA(cudaMemcpyAsync(dist_out, h->tmp_dist, h->d.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return RBP_OK;
+}
+
+int rbp_kmeans_centroids(rbp_kmeans_t* h, uint64_t* counts_out, uint64_t* weights_out) {
+    if (!h) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    std::vector<unsigned long long> host((size_t)h->d.k * (kBins + 1));
+    RBP_CUDA(cudaMemcpyAsync(host.data(), h->d.ccount, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < h->d.k; ++j) {
+        if (counts_out) for (int b = 0; b < kBins; ++b) counts_out[(size_t)j * kBins + b] = host[(size_t)j * (kBins + 1) + b];
+        if (weights_out) weights_out[j] = host[(size_t)j * (kBins + 1) + kBins];
+    }
+    return RBP_OK;
+}
+
+int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out) {
+    if (!h || !tri_out) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    const int total = h->d.k * (h->d.k - 1) / 2;
+    if (total == 0) return RBP_OK;
+    metric_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d.cdf, h->d.k, h->tri);
+    RBP_LAUNCHED();
+    metric_normalize_kernel<<<1, 256, 0, h->stream>>>(h->tri, total);
+    RBP_LAUNCHED();
+    RBP_CUDA(cudaMemcpyAsync(tri_out, h->tri, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return RBP_OK;
+}
+
+int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out) {
+    if (!h) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    KmDev& d = h->d;
+    if (d.pending) {
+        materialize_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, h->stream>>>(d);
+        RBP_LAUNCHED();
+        d.pending = 0;
+    }
+    if (assign_out) RBP_CUDA(cudaMemcpyAsync(assign_out, d.assign, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (upper_out) RBP_CUDA(cudaMemcpyAsync(upper_out, d.upper, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (stale_out) RBP_CUDA(cudaMemcpyAsync(stale_out, d.stale, d.n, cudaMemcpyDeviceToHost, h->stream));
+    if (lower_out) {  // device layout is [K][N]; the reference's Bounds is per point: transpose on the host
+        std::vector<float> kn((size_t)d.k * d.n);
+        RBP_CUDA(cudaMemcpyAsync(kn.data(), d.lower, kn.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+        RBP_CUDA(cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < d.n; ++i)
+            for (int j = 0; j < d.k; ++j) lower_out[(size_t)i * d.k + j] = kn[(size_t)j * d.n + i];
+    }
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return RBP_OK;
+}
+
+int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out) {
+    // what: 0 = full step, 1 = assign (N x K distances), device time by CUDA events on the library stream
+    if (!h || !ms_out || iters < 1) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    RBP_CUDA(cudaEventCreate(&e0));
+    RBP_CUDA(cudaEventCreate(&e1));
+    RBP_CUDA(cudaEventRecord(e0, h->stream));
+    for (int it = 0; it < iters; ++it) {
+        int st;
+        if (what == 0) st = rbp_kmeans_step(h, nullptr, nullptr, nullptr);
+        else {
+            assign_kernel<false><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+            g_launches.fetch_add(1);
+            st = cudaGetLastError() == cudaSuccess ? RBP_OK : RBP_ERR_CUDA;
+        }
+        if (st) return st;
+    }
+    RBP_CUDA(cudaEventRecord(e1, h->stream));
+    RBP_CUDA(cudaEventSynchronize(e1));
+    RBP_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return RBP_OK;
+}
+
+}  // extern "C"

@@ -366,12 +366,13 @@ __device__ __forceinline__ float regret_gain(const RegretConst& c, float net, fl
 // (Markstein's theorem) whenever no intermediate under/overflows and b's significand is not all ones — both
 // guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
 __device__ __forceinline__ float div_by_count(float a, float b, float rb) {
-    const float aa = fabsf(a);
-    const bool safe = aa > 1.0e-18f && aa < 1.0e18f && (__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu;
-    if (!safe) return a / b;
+    // exponent of a within [2^-64, 2^63] (zero takes the slow path too), evaluated beside the FMA chain
+    const bool safe = ((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u && (__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu;
     const float q = a * rb;
     const float r = __fmaf_rn(-b, q, a);
-    return __fmaf_rn(r, rb, q);
+    const float fast = __fmaf_rn(r, rb, q);
+    if (__builtin_expect(!safe, 0)) return a / b;
+    return fast;
 }
 
 template <int RS, int WS, bool MASKED>
@@ -436,6 +437,15 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
         ev = table[row + lane].payoff;
         visits = table[row + lane].visits;
     }
+    // rows of one infoset are always visited together, so their visit counters agree unless a profile with
+    // unequal counters was imported; the shared reciprocal table below needs them equal
+    const uint32_t visits0 = __shfl_sync(0xFFFFFFFFu, visits, 0);
+    const bool uniform_visits = __all_sync(0xFFFFFFFFu, lane >= A || visits == visits0);
+    float* s_cnt = reinterpret_cast<float*>(s_mask + kFoldCap);  // [kFoldCap] (float)(visits+1)   (warp 2)
+    float* s_rcp = s_cnt + kFoldCap;                             // [kFoldCap] RN(1/(visits+1))    (warp 2)
+    __shared__ int s_pfx[3][33];
+    __shared__ uint32_t s_src[3][32];
+    uint32_t done = 0;
     for (int c = 0; c < sc.nblk; c += kFoldChunkBlocks) {
         const int b = c + lane;
         const int n_mine = b < sc.nblk ? cnt[b] : 0;
@@ -447,19 +457,69 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
         }
         const int chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const int p_mine = incl - n_mine;
-        // stage the chunk: segment s = this infoset's records of tree-block c+s, contiguous and in tree order
-        for (int sgm = 0; sgm < kFoldChunkBlocks; ++sgm) {
-            const int ns = __shfl_sync(0xFFFFFFFFu, n_mine, sgm);
-            const int os = __shfl_sync(0xFFFFFFFFu, o_mine, sgm);
-            const int ps = __shfl_sync(0xFFFFFFFFu, p_mine, sgm);
-            const size_t base = (size_t)(c + sgm) * sc.cap + os;
-            for (int i = lane; i < ns; i += 32) {
-                if (warp == 0) {
-                    for (int k = 0; k < A; ++k) s_dr[k * kFoldCap + ps + i] = sc.dr[(size_t)k * total + base + i];
-                    if (MASKED) s_mask[ps + i] = sc.mask[base + i];
+        // stage the chunk into shared memory: segment s = this infoset's records of tree-block c+s (contiguous,
+        // tree order).  Each lane resolves flat chunk positions to (segment, offset) by a 5-step search over the
+        // segment prefix, so a batch of independent loads is in flight before the first store.
+        s_pfx[warp][lane] = p_mine;
+        s_src[warp][lane] = (uint32_t)((size_t)b * sc.cap + o_mine);
+        if (lane == 0) s_pfx[warp][32] = chunk_total;
+        __syncwarp();
+        constexpr int U = 4;
+        for (int e0 = 0; e0 < chunk_total; e0 += 32 * U) {
+            uint32_t src[U];
+            float v0[U], v1[U], v2[U], v3[U];
+            uint8_t mk[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * 32 + lane;
+                int sg = 0;
+                if (e < chunk_total) {
+                    if (s_pfx[warp][16] <= e) sg = 16;
+                    if (s_pfx[warp][sg + 8] <= e) sg += 8;
+                    if (s_pfx[warp][sg + 4] <= e) sg += 4;
+                    if (s_pfx[warp][sg + 2] <= e) sg += 2;
+                    if (s_pfx[warp][sg + 1] <= e) sg += 1;
+                    src[u] = s_src[warp][sg] + (uint32_t)(e - s_pfx[warp][sg]);
                 } else {
-                    s_pay[ps + i] = sc.pay[base + i];
+                    src[u] = 0xFFFFFFFFu;
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v0[u] = v1[u] = v2[u] = v3[u] = 0.0f; mk[u] = 0;
+                if (src[u] != 0xFFFFFFFFu) {
+                    if (warp == 0) {
+                        v0[u] = sc.dr[src[u]];
+                        if (A > 1) v1[u] = sc.dr[total + src[u]];
+                        if (A > 2) v2[u] = sc.dr[2 * total + src[u]];
+                        if (A > 3) v3[u] = sc.dr[3 * total + src[u]];
+                        if (MASKED) mk[u] = sc.mask[src[u]];
+                    } else {
+                        v0[u] = sc.pay[src[u]];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * 32 + lane;
+                if (src[u] != 0xFFFFFFFFu) {
+                    if (warp == 0) {
+                        s_dr[e] = v0[u];
+                        if (A > 1) s_dr[kFoldCap + e] = v1[u];
+                        if (A > 2) s_dr[2 * kFoldCap + e] = v2[u];
+                        if (A > 3) s_dr[3 * kFoldCap + e] = v3[u];
+                        if (MASKED) s_mask[e] = mk[u];
+                    } else {
+                        s_pay[e] = v0[u];
+                    }
+                }
+            }
+        }
+        if (warp == 2 && uniform_visits) {  // divisors and their reciprocals for this chunk, all lanes, off the chain
+            for (int e = lane; e < chunk_total; e += 32) {
+                const float bc = (float)(visits0 + done + (uint32_t)e + 1u);
+                s_cnt[e] = bc;
+                s_rcp[e] = __frcp_rn(bc);
             }
         }
         __syncwarp();
@@ -470,16 +530,18 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
                 for (int e = 0; e < chunk_total; ++e) {
                     if (!MASKED || (s_mask[e] >> lane & 1u)) { R = regret_gain<RS>(rc, R, d[e]); ++ups; }
                 }
-            } else {  // solver.rs:174-192 update_payoff (Welford) then update_visits
-#pragma unroll 4
+            } else if (uniform_visits) {  // solver.rs:174-192 update_payoff (Welford) then update_visits
+#pragma unroll 8
+                for (int e = 0; e < chunk_total; ++e) ev += div_by_count(s_pay[e] - ev, s_cnt[e], s_rcp[e]);
+                visits += (uint32_t)chunk_total;
+            } else {
                 for (int e = 0; e < chunk_total; ++e) {
-                    const float bcount = (float)(visits + 1u);
-                    const float rb = __frcp_rn(bcount);
-                    ev += div_by_count(s_pay[e] - ev, bcount, rb);
+                    ev += (s_pay[e] - ev) / (float)(visits + 1u);
                     visits += 1u;
                 }
             }
         }
+        done += (uint32_t)chunk_total;
         __syncwarp();
     }
     if (lane < A) {
@@ -810,7 +872,7 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
         return fail(RBP_ERR_CUDA);
     int max_a = 1;
     for (uint8_t na : G.info_actions) max_a = std::max<int>(max_a, na);
-    s->fold_smem = (size_t)kFoldCap * ((max_a + 1) * sizeof(float) + 1);
+    s->fold_smem = (size_t)kFoldCap * ((max_a + 3) * sizeof(float) + 1);
     if ((st = fold_attr(s->fold_smem))) return fail(st);
     *out = s;
     return RBP_OK;
