@@ -41,6 +41,10 @@ def lib():
         l.orc_solver_import.argtypes = [vp, vp, i32, u64]
         l.orc_solver_averaged.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_float)]
         l.orc_solver_set_hyper.argtypes = [vp] + [ctypes.c_float] * 5 + [u32, ctypes.c_float]
+        l.orc_solver_set_fold.argtypes = [vp, i32, i32, i32]
+        l.orc_solver_partial_words.argtypes = [vp]
+        l.orc_solver_sample.argtypes = [vp, vp]
+        l.orc_solver_fold_gathered.argtypes = [vp, vp, i32]
         l.orc_philox.argtypes = [u32] * 6 + [ctypes.POINTER(u32)]
         _lib = l
     return _lib
@@ -70,6 +74,22 @@ class OracleSolver:
         h.update(kw)
         lib().orc_solver_set_hyper(self._h, h["temperature"], h["smoothing"], h["curiosity"], h["prune_threshold"],
                                    h["prune_explore"], h["prune_warmup"], h["regret_min"])
+
+    def set_fold(self, fold_mode, world_rank=0, world_size=1):
+        lib().orc_solver_set_fold(self._h, fold_mode, world_rank, world_size)
+
+    def partial_words(self):
+        return lib().orc_solver_partial_words(self._h)
+
+    def sample(self):
+        """BATCHED fold, first half: this rank's blocked partial sums as a u32 word buffer."""
+        out = np.zeros(self.partial_words(), dtype=np.uint32)
+        lib().orc_solver_sample(self._h, out.ctypes.data)
+        return out
+
+    def fold_gathered(self, words, world):
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        lib().orc_solver_fold_gathered(self._h, words.ctypes.data, world)
 
     def step(self, n=1):
         lib().orc_solver_step(self._h, n)

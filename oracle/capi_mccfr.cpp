@@ -97,6 +97,22 @@ void orc_solver_set_hyper(OrcSolver* s, float temperature, float smoothing, floa
         return 0;
     });
 }
+void orc_solver_set_fold(OrcSolver* s, int fold_mode, int world_rank, int world_size) {
+    with(s, [&](auto& sv) { sv.fold_mode = fold_mode; sv.world_rank = world_rank; sv.world_size = world_size; return 0; });
+}
+int orc_solver_partial_words(OrcSolver* s) {
+    return with(s, [](auto& sv) { sv.ensure_info_order(); return (int)(sv.info_order.size() * sizeof(Partial) / 4); });
+}
+void orc_solver_sample(OrcSolver* s, uint32_t* words_out) {
+    with(s, [&](auto& sv) {
+        std::vector<Partial> p = sv.sample_partials();
+        std::memcpy(words_out, p.data(), p.size() * sizeof(Partial));
+        return 0;
+    });
+}
+void orc_solver_fold_gathered(OrcSolver* s, const uint32_t* words, int world) {
+    with(s, [&](auto& sv) { sv.fold_gathered(reinterpret_cast<const Partial*>(words), world); return 0; });
+}
 // averaged policy (Nash approximation) for one infoset: profile.rs:41-45
 int orc_solver_averaged(OrcSolver* s, uint32_t info_key, float* out) {
     return with(s, [&](auto& sv) {

@@ -16,6 +16,7 @@
 //   sample/{external,pruning,pluribus,vanilla,mod}.rs samplers
 //   regret/*.rs, policy/*.rs                          schedules
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -204,8 +205,20 @@ struct Tree {  // state/tree.rs + petgraph::Graph adjacency (newest out-edge fir
     }
 };
 
+// BATCHED fold (include/rbp.h RBP_FOLD_BATCHED; not a reference mode — the north-star's "allreduce of deltas" form):
+// per epoch and infoset the Decisions of all trees are summed in a fixed blocked order (sequentially inside blocks
+// of 128 trees, then over a rank's blocks, then over ranks) and every schedule is applied ONCE per row.
+struct Partial {  // 12 words per infoset, the unit ranks exchange
+    float dr[MAXA];
+    float pay;
+    uint32_t n;
+    uint32_t na[MAXA];
+    uint32_t pad[2];
+};
+
 struct Decisions {  // solver/decisions.rs:23-32
     uint32_t info;
+    int tree;              // global tree id
     int n;                 // choices
     bool explored[MAXA];
     float regret[MAXA];    // only where explored
@@ -219,6 +232,8 @@ struct Solver {
     Profile<G> profile;
     int regret_sched = R_FLOORED, weight_sched = W_LINEAR, sampling = S_EXTERNAL;
     int batch = 1, threads = 1, fold_mode = FOLD_ORDERED, fold_block = 128;
+    int world_rank = 0, world_size = 1;
+    std::vector<uint32_t> info_order;  // all decision infosets of the game, ascending key: index space of Partial buffers
     Draw rng{0};
     // telemetry (metrics/mod.rs: nodes / infos counters)
     uint64_t nodes = 0, infos = 0, updates = 0;
@@ -383,6 +398,7 @@ struct Solver {
         for (size_t i = 0; i < keys.size(); ++i) {
             if ((int)G::turn(tree.game[spans[i][0]]) != walker) continue;
             out.push_back(update_vector(tree, spans[i]));
+            out.back().tree = tree.id;
         }
     }
 
@@ -399,7 +415,8 @@ struct Solver {
         auto work = [&](int t) {
             int lo = (int)((int64_t)batch * t / T), hi = (int)((int64_t)batch * (t + 1) / T);
             for (int i = lo; i < hi; ++i) {
-                Tree<G> tree = build(root_of(i), i, sampling);
+                const int id = world_rank * batch + i;
+                Tree<G> tree = build(root_of(id), id, sampling);
                 ncount[t] += tree.n();
                 tree_decisions(tree, parts[t]);
             }
@@ -438,8 +455,90 @@ struct Solver {
         for (int a = 0; a < d.n; ++a) profile.mut_row(d.info, a).visits += 1;
     }
 
+    void ensure_info_order() {
+        if (!info_order.empty()) return;
+        Tree<G> tree = build(G::exploitability_root(), 0, S_VANILLA);
+        for (int n = 0; n < tree.n(); ++n) {
+            Turn t = G::turn(tree.game[n]);
+            if (tree.head[n] >= 0 && (t == TURN_P0 || t == TURN_P1)) info_order.push_back(tree.info[n]);
+        }
+        std::sort(info_order.begin(), info_order.end());
+        info_order.erase(std::unique(info_order.begin(), info_order.end()), info_order.end());
+    }
+    int info_index(uint32_t key) const {
+        return (int)(std::lower_bound(info_order.begin(), info_order.end(), key) - info_order.begin());
+    }
+    // this rank's blocked partial sums for the current epoch (K1 + block/rank reduction on the GPU)
+    std::vector<Partial> sample_partials() {
+        ensure_info_order();
+        uint64_t nc = 0;
+        std::vector<Decisions> all = run_batch(&nc);
+        nodes += nc;
+        infos += all.size();
+        const size_t I = info_order.size();
+        std::vector<Partial> rank(I), block(I);
+        std::vector<uint8_t> touched(I, 0);
+        auto zero = [](Partial& p) { std::memset(&p, 0, sizeof p); };
+        for (auto& p : rank) zero(p);
+        for (auto& p : block) zero(p);
+        auto flush = [&]() {  // rank += block, every infoset (dense adds, exactly what the device kernel does)
+            for (size_t x = 0; x < I; ++x) {
+                for (int a = 0; a < MAXA; ++a) { rank[x].dr[a] = rank[x].dr[a] + block[x].dr[a]; rank[x].na[a] += block[x].na[a]; }
+                rank[x].pay = rank[x].pay + block[x].pay;
+                rank[x].n += block[x].n;
+                zero(block[x]);
+            }
+        };
+        int cur = 0;
+        for (const Decisions& d : all) {
+            int b = (d.tree - world_rank * batch) / fold_block;
+            while (cur < b) { flush(); ++cur; }
+            Partial& k = block[info_index(d.info)];
+            for (int a = 0; a < d.n; ++a)
+                if (d.explored[a]) { k.dr[a] = k.dr[a] + d.regret[a]; k.na[a] += 1; }
+            k.pay = k.pay + d.payoff;
+            k.n += 1;
+        }
+        const int nblk = (batch + fold_block - 1) / fold_block;
+        while (cur < nblk) { flush(); ++cur; }
+        return rank;
+    }
+    // sum the ranks' partials in rank order and apply each schedule once per row; advances the epoch
+    void fold_gathered(const Partial* gathered, int world) {
+        ensure_info_order();
+        const size_t I = info_order.size();
+        const uint64_t epoch = profile.epochs;
+        for (size_t x = 0; x < I; ++x) {
+            Partial t;
+            std::memset(&t, 0, sizeof t);
+            for (int r = 0; r < world; ++r) {
+                const Partial& g = gathered[(size_t)r * I + x];
+                for (int a = 0; a < MAXA; ++a) { t.dr[a] = t.dr[a] + g.dr[a]; t.na[a] += g.na[a]; }
+                t.pay = t.pay + g.pay;
+                t.n += g.n;
+            }
+            if (t.n == 0) continue;
+            const uint32_t info = info_order[x];
+            InfoView v = view_of(profile, info);  // regret matching on the pre-fold regrets
+            for (int a = 0; a < v.n; ++a) {
+                Encounter& e = profile.mut_row(info, a);
+                if (t.na[a] > 0) { e.regret = regret_gain(regret_sched, e.regret, t.dr[a], epoch, profile.hyper); updates += t.na[a]; }
+                e.weight = weight_learn(weight_sched, e.weight, (float)t.n * (v.r[a] / v.rd), epoch);
+                const float mean = t.pay / (float)t.n;
+                e.payoff += (mean - e.payoff) * (float)t.n / (float)(e.visits + t.n);
+                e.visits += t.n;
+            }
+        }
+        profile.epochs += 1;
+    }
+
     // solver.rs:96-105 step
     void step() {
+        if (fold_mode == FOLD_BATCHED) {
+            std::vector<Partial> mine = sample_partials();
+            fold_gathered(mine.data(), 1);
+            return;
+        }
         uint64_t nc = 0;
         std::vector<Decisions> all = run_batch(&nc);
         nodes += nc;

@@ -70,13 +70,25 @@ struct Scratch {        // per-epoch Decisions, block-sorted by infoset
     int32_t* m_cnt;     // [I][nblk]
     unsigned long long* counters;  // nodes, infos, updates
     int nblk, cap;      // cap = records per block
+    // BATCHED fold: per-block partial sums, [field][I][nblk]; fields 0-3 regret deltas, 4 payoff / explored counts
+    float* bp_f;        // [5][I][nblk]
+    uint32_t* bp_na;    // [4][I][nblk]
+};
+
+// BATCHED fold exchange unit, 12 words per infoset (include/rbp.h rbp_solver_delta_buffer)
+struct Partial {
+    float dr[kMaxActions];
+    float pay;
+    uint32_t n;
+    uint32_t na[kMaxActions];
+    uint32_t pad[2];
 };
 
 struct EpochArgs {
     uint32_t seed_lo, seed_hi, epoch;
     int walker, batch, tree_base, sampling;
     rbp_hyper_t hyper;
-    int regret_sched, weight_sched;
+    int regret_sched, weight_sched, fold_mode;
     float t;                // epoch as f32
     float disc_pos, disc_neg;  // DiscountedRegret x = t^1.5, t^0.5 (host libm, regret/discounted.rs:33,37)
 };
@@ -327,6 +339,27 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
         sc.m_off[(size_t)x * sc.nblk + blockIdx.x] = (int32_t)s_off[x];
         sc.m_cnt[(size_t)x * sc.nblk + blockIdx.x] = (int32_t)s_cnt[x];
     }
+    if (ep.fold_mode == RBP_FOLD_BATCHED) {
+        // per-block sums of this block's Decisions, sequential in tree order (the innermost level of the blocked order)
+        __syncthreads();
+        for (int x = tid; x < I; x += kTreesPerBlock) {
+            const int n = (int)s_cnt[x], A = g.info_actions[x];
+            float dr[kMaxActions] = {0.0f, 0.0f, 0.0f, 0.0f}, pay = 0.0f;
+            uint32_t na[kMaxActions] = {0u, 0u, 0u, 0u};
+            const size_t first = base + s_off[x];
+            for (int e = 0; e < n; ++e) {
+                const uint32_t m = sc.mask[first + e];
+                for (int a = 0; a < A; ++a)
+                    if (m >> a & 1u) { dr[a] = dr[a] + sc.dr[(size_t)a * total + first + e]; na[a] += 1u; }
+                pay = pay + sc.pay[first + e];
+            }
+            for (int a = 0; a < kMaxActions; ++a) {
+                sc.bp_f[((size_t)a * I + x) * sc.nblk + blockIdx.x] = dr[a];
+                sc.bp_na[((size_t)a * I + x) * sc.nblk + blockIdx.x] = na[a];
+            }
+            sc.bp_f[((size_t)kMaxActions * I + x) * sc.nblk + blockIdx.x] = pay;
+        }
+    }
     // telemetry (metrics/mod.rs): nodes, infosets
     unsigned long long nn = (unsigned long long)ln, ni = (unsigned long long)nrec;
     for (int d = 16; d > 0; d >>= 1) {
@@ -555,6 +588,83 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
     }
 }
 
+// ───────────────────────────── K3b: BATCHED fold ─────────────────────────────
+// rank level of the blocked order: one warp per infoset, lane f sums field f over this rank's tree-blocks in order
+__global__ void __launch_bounds__(32)
+mccfr_rank_partial_kernel(DevGame g, Scratch sc, Partial* __restrict__ out) {
+    const int x = blockIdx.x, lane = threadIdx.x, I = g.n_infos;
+    if (lane < kMaxActions + 1) {
+        const float* src = sc.bp_f + ((size_t)lane * I + x) * sc.nblk;
+        float acc = 0.0f;
+        for (int b = 0; b < sc.nblk; ++b) acc = acc + src[b];
+        if (lane < kMaxActions) out[x].dr[lane] = acc; else out[x].pay = acc;
+    } else if (lane < 2 * kMaxActions + 1) {
+        const int a = lane - (kMaxActions + 1);
+        const uint32_t* src = sc.bp_na + ((size_t)a * I + x) * sc.nblk;
+        uint32_t acc = 0;
+        for (int b = 0; b < sc.nblk; ++b) acc += src[b];
+        out[x].na[a] = acc;
+    } else if (lane == 2 * kMaxActions + 1) {
+        const int32_t* src = sc.m_cnt + (size_t)x * sc.nblk;
+        uint32_t acc = 0;
+        for (int b = 0; b < sc.nblk; ++b) acc += (uint32_t)src[b];
+        out[x].n = acc;
+        out[x].pad[0] = out[x].pad[1] = 0u;
+    }
+}
+__device__ __forceinline__ float regret_gain_rt(const EpochArgs& ep, float net, float add) {
+    RegretConst rc;
+    rc.d_lin = ep.t / (ep.t + 1.0f);
+    rc.d_pos = ep.disc_pos / (ep.disc_pos + 1.0f);
+    rc.d_neg = ep.disc_neg / (ep.disc_neg + 1.0f);
+    rc.d_zero = rc.d_lin;
+    switch (ep.regret_sched) {
+        case RBP_REGRET_SUMMED: rc.floor = -INFINITY; return regret_gain<RBP_REGRET_SUMMED>(rc, net, add);
+        case RBP_REGRET_FLOORED: rc.floor = 0.0f; return regret_gain<RBP_REGRET_FLOORED>(rc, net, add);
+        case RBP_REGRET_LINEAR: rc.floor = ep.hyper.regret_min; return regret_gain<RBP_REGRET_LINEAR>(rc, net, add);
+        case RBP_REGRET_DISCOUNTED: rc.floor = ep.hyper.regret_min; return regret_gain<RBP_REGRET_DISCOUNTED>(rc, net, add);
+        default: rc.floor = ep.hyper.regret_min; return regret_gain<RBP_REGRET_ASYMMETRIC>(rc, net, add);
+    }
+}
+// world level + schedules: sum the ranks' partials in rank order, then ONE schedule application per row
+__global__ void __launch_bounds__(128)
+mccfr_apply_batched_kernel(DevGame g, rbp_encounter_t* __restrict__ table, const Partial* __restrict__ gathered, int world,
+                           EpochArgs ep, unsigned long long* __restrict__ counters) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, I = g.n_infos;
+    if (x >= I) return;
+    float dr[kMaxActions] = {0.0f, 0.0f, 0.0f, 0.0f}, pay = 0.0f;
+    uint32_t na[kMaxActions] = {0u, 0u, 0u, 0u}, n = 0;
+    for (int r = 0; r < world; ++r) {
+        const Partial p = gathered[(size_t)r * I + x];
+        for (int a = 0; a < kMaxActions; ++a) { dr[a] = dr[a] + p.dr[a]; na[a] += p.na[a]; }
+        pay = pay + p.pay;
+        n += p.n;
+    }
+    if (n == 0) return;
+    const int A = g.info_actions[x], row = g.info_row[x];
+    float r[kMaxActions], rd = 0.0f;
+    for (int a = 0; a < A; ++a) { r[a] = fmax_ref(table[row + a].regret, kEps); rd = rd + r[a]; }
+    unsigned long long ups = 0;
+    for (int a = 0; a < A; ++a) {
+        rbp_encounter_t e = table[row + a];
+        if (na[a] > 0) { e.regret = regret_gain_rt(ep, e.regret, dr[a]); ups += na[a]; }
+        const float add = (float)n * (r[a] / rd);
+        float acc;
+        switch (ep.weight_sched) {
+            case RBP_WEIGHT_CONSTANT: acc = e.weight + add; break;
+            case RBP_WEIGHT_LINEAR: acc = e.weight + add * ep.t; break;
+            case RBP_WEIGHT_QUADRATIC: acc = e.weight + add * ep.t * ep.t; break;
+            default: acc = e.weight * 0.9999f + add; break;
+        }
+        e.weight = fmax_ref(acc, kEps);
+        const float mean = pay / (float)n;
+        e.payoff += (mean - e.payoff) * (float)n / (float)(e.visits + n);
+        e.visits += n;
+        table[row + a] = e;
+    }
+    if (ups) atomicAdd(&counters[2], ups);
+}
+
 // self-test of div_by_count against IEEE division: every count b in [1, max_count] against `samples` dividends
 // (Philox bits reinterpreted so that all exponents in the guarded range, both signs, occur)
 __global__ void div_selftest_kernel(uint32_t max_count, uint32_t samples, unsigned long long* mismatches) {
@@ -685,6 +795,7 @@ struct rbp_solver {
     rbp_hyper_t hyper{};
     size_t sample_smem = 0, fold_smem = 0;
     uint4* flush_buf = nullptr;
+    Partial* delta = nullptr;  // this rank's BATCHED partial sums
     std::vector<cudaEvent_t> events;
 };
 
@@ -716,7 +827,7 @@ EpochArgs epoch_args(const rbp_solver* s) {
     ep.tree_base = s->world_rank * s->batch;
     ep.sampling = s->sampling;
     ep.hyper = s->hyper;
-    ep.regret_sched = s->regret; ep.weight_sched = s->weight;
+    ep.regret_sched = s->regret; ep.weight_sched = s->weight; ep.fold_mode = s->fold_mode;
     ep.t = (float)s->epochs;
     ep.disc_pos = powf(ep.t / 1.0f, 1.5f);
     ep.disc_neg = powf(ep.t / 1.0f, 0.5f);
@@ -724,6 +835,16 @@ EpochArgs epoch_args(const rbp_solver* s) {
 }
 int launch_sample(rbp_solver* s, const EpochArgs& ep) {
     mccfr_sample_kernel<<<s->sc.nblk, kTreesPerBlock, s->sample_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+int launch_rank_partial(rbp_solver* s) {
+    mccfr_rank_partial_kernel<<<s->dev.n_infos, 32, 0, s->stream>>>(s->dev, s->sc, s->delta);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+int launch_apply_batched(rbp_solver* s, const EpochArgs& ep, const Partial* gathered, int world) {
+    mccfr_apply_batched_kernel<<<(s->dev.n_infos + 127) / 128, 128, 0, s->stream>>>(s->dev, s->table, gathered, world, ep, s->sc.counters);
     RBP_LAUNCHED();
     return RBP_OK;
 }
@@ -820,7 +941,7 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
         set_last_error("training needs a sampling scheme (VanillaSampling is exploitability-only, sample/vanilla.rs)");
         return RBP_ERR_INVALID;
     }
-    if (fold_mode != RBP_FOLD_ORDERED) { set_last_error("fold mode not built yet"); return RBP_ERR_INVALID; }
+    if (fold_mode != RBP_FOLD_ORDERED && fold_mode != RBP_FOLD_BATCHED) return RBP_ERR_INVALID;
     if (rbp_device_count() <= device) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
     rbp_solver* s = new rbp_solver();
     if (!build_flat_game(game, &s->game)) { delete s; return RBP_ERR_INVALID; }
@@ -863,6 +984,11 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
     if ((st = alloc(s, (size_t)d.n_infos * sc.nblk, &sc.m_off))) return fail(st);
     if ((st = alloc(s, (size_t)d.n_infos * sc.nblk, &sc.m_cnt))) return fail(st);
     if ((st = alloc(s, 3, &sc.counters))) return fail(st);
+    if (fold_mode == RBP_FOLD_BATCHED) {
+        if ((st = alloc(s, (size_t)5 * d.n_infos * sc.nblk, &sc.bp_f))) return fail(st);
+        if ((st = alloc(s, (size_t)4 * d.n_infos * sc.nblk, &sc.bp_na))) return fail(st);
+        if ((st = alloc(s, (size_t)d.n_infos, &s->delta))) return fail(st);
+    }
     if ((st = alloc(s, (size_t)d.n_nodes, &s->U))) return fail(st);
     if ((st = alloc(s, (size_t)d.n_infos * kMaxActions, &s->cfv))) return fail(st);
     if ((st = alloc(s, (size_t)d.n_infos, &s->br))) return fail(st);
@@ -896,11 +1022,18 @@ void rbp_solver_destroy(rbp_solver_t* s) {
 int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs) {
     if (!s) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(s->device));
+    if (s->fold_mode == RBP_FOLD_BATCHED && s->world_size > 1) {
+        set_last_error("BATCHED fold with world_size > 1: drive rbp_solver_sample / exchange / rbp_solver_fold_gathered");
+        return RBP_ERR_STATE;
+    }
     for (uint64_t i = 0; i < n_epochs; ++i) {
         EpochArgs ep = epoch_args(s);
         int st;
         if ((st = launch_sample(s, ep))) return st;
-        if ((st = launch_fold(s, ep))) return st;
+        if (s->fold_mode == RBP_FOLD_BATCHED) {
+            if ((st = launch_rank_partial(s))) return st;
+            if ((st = launch_apply_batched(s, ep, s->delta, 1))) return st;
+        } else if ((st = launch_fold(s, ep))) return st;
         s->epochs += 1;  // book.rs:138-140
     }
     RBP_CUDA(cudaStreamSynchronize(s->stream));
@@ -930,7 +1063,11 @@ int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, floa
         RBP_CUDA(cudaEventRecord(s->events[3 * i], s->stream));
         if ((st = launch_sample(s, ep))) return st;
         RBP_CUDA(cudaEventRecord(s->events[3 * i + 1], s->stream));
-        if ((st = launch_fold(s, ep))) return st;
+        if (s->fold_mode == RBP_FOLD_BATCHED) {
+            if (s->world_size > 1) return RBP_ERR_STATE;
+            if ((st = launch_rank_partial(s))) return st;
+            if ((st = launch_apply_batched(s, ep, s->delta, 1))) return st;
+        } else if ((st = launch_fold(s, ep))) return st;
         RBP_CUDA(cudaEventRecord(s->events[3 * i + 2], s->stream));
         s->epochs += 1;
     }
@@ -1056,8 +1193,34 @@ int rbp_solver_game_shape(rbp_solver_t* s, int out[6]) {
     return RBP_OK;
 }
 
-int rbp_solver_sample(rbp_solver_t*) { set_last_error("not built yet"); return RBP_ERR_STATE; }
-int rbp_solver_delta_buffer(rbp_solver_t*, void**, size_t*) { set_last_error("not built yet"); return RBP_ERR_STATE; }
-int rbp_solver_fold_gathered(rbp_solver_t*, const void*, int) { set_last_error("not built yet"); return RBP_ERR_STATE; }
+int rbp_solver_sample(rbp_solver_t* s) {
+    if (!s) return RBP_ERR_INVALID;
+    if (s->fold_mode != RBP_FOLD_BATCHED) { set_last_error("rbp_solver_sample needs RBP_FOLD_BATCHED"); return RBP_ERR_STATE; }
+    RBP_CUDA(cudaSetDevice(s->device));
+    EpochArgs ep = epoch_args(s);
+    int st;
+    if ((st = launch_sample(s, ep))) return st;
+    if ((st = launch_rank_partial(s))) return st;
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
+int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes) {
+    if (!s || !dev_ptr || !bytes) return RBP_ERR_INVALID;
+    if (s->fold_mode != RBP_FOLD_BATCHED) return RBP_ERR_STATE;
+    *dev_ptr = s->delta;
+    *bytes = (size_t)s->dev.n_infos * sizeof(Partial);
+    return RBP_OK;
+}
+int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size) {
+    if (!s || !dev_gathered || world_size < 1) return RBP_ERR_INVALID;
+    if (s->fold_mode != RBP_FOLD_BATCHED) return RBP_ERR_STATE;
+    RBP_CUDA(cudaSetDevice(s->device));
+    EpochArgs ep = epoch_args(s);
+    int st;
+    if ((st = launch_apply_batched(s, ep, static_cast<const Partial*>(dev_gathered), world_size))) return st;
+    s->epochs += 1;
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,83 @@
+"""One process per GPU: the single exchange step of the hot path, over torch.distributed.
+
+MCCFR (BATCHED fold): every rank samples its shard of the epoch's trees and reduces it to blocked partial sums
+(`sample`), ranks all-gather those 48-byte-per-infoset partials (NCCL over NVLink on GPUs, gloo in the CPU tests), and
+every rank folds the gathered buffer in rank order (`fold_gathered`) — so all tables stay bit-identical without ever
+moving per-tree records.  k-means: integer centroid accumulators are all-reduced (sum) between `step_local` and
+`step_finish`.
+
+The solver object only needs `sample() / fold_gathered()`; the GPU `Solver` and the CPU oracle both provide them, which
+is how the world_size-2 gloo tests exercise this file without a GPU.
+"""
+import numpy as np
+
+
+class _DeviceWords:
+    """Zero-copy view of library-owned device memory for torch (`__cuda_array_interface__`)."""
+
+    def __init__(self, ptr, nbytes, typestr="<u4", itemsize=4):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedSolver:
+    """`Solver::step` across `world_size` ranks; rank r owns tree ids [r*batch, (r+1)*batch) of each epoch."""
+
+    def __init__(self, solver, dist=None, device=None):
+        import torch
+
+        self.solver = solver
+        self.dist = dist
+        self.torch = torch
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.on_gpu = hasattr(solver, "delta_buffer")
+        if self.on_gpu:
+            solver.set_world(self.rank, self.world)
+            ptr, nbytes = solver.delta_buffer()
+            self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+            self.local = torch.as_tensor(_DeviceWords(ptr, nbytes), device=self.device)
+            self.gathered = torch.empty(self.world * self.local.numel(), dtype=self.local.dtype, device=self.device)
+        else:
+            solver.set_fold(1, self.rank, self.world)
+            self.gathered = torch.empty(self.world * solver.partial_words(), dtype=torch.int32)
+
+    def step(self, n=1):
+        torch = self.torch
+        for _ in range(n):
+            if self.on_gpu:
+                self.solver.sample()  # returns with the library stream drained
+                if self.dist is not None and self.world > 1:
+                    self.dist.all_gather_into_tensor(self.gathered, self.local)
+                    torch.cuda.current_stream(self.device).synchronize()
+                else:
+                    self.gathered.copy_(self.local)
+                    torch.cuda.current_stream(self.device).synchronize()
+                self.solver.fold_gathered(self.gathered.data_ptr(), self.world)
+            else:
+                words = torch.from_numpy(self.solver.sample().view(np.int32))
+                if self.dist is not None and self.world > 1:
+                    self.dist.all_gather_into_tensor(self.gathered, words)
+                else:
+                    self.gathered.copy_(words)
+                self.solver.fold_gathered(self.gathered.numpy().view(np.uint32), self.world)
+        return self
+
+
+def allreduce_kmeans_step(layer, dist, device=None):
+    """`Elkan::step_elkan` for point-sharded ranks: local point pass, integer all-reduce of the centroid
+    accumulators and tallies, then the centroid/drift update — identical on every rank."""
+    import torch
+
+    layer.step_local()
+    acc_ptr, acc_bytes, sizes_ptr, re_ptr, _ = layer.exchange_buffers()
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    acc = torch.as_tensor(_DeviceWords(acc_ptr, acc_bytes, "<i8", 8), device=dev)
+    sizes = torch.as_tensor(_DeviceWords(sizes_ptr, 4 * layer.k, "<i4", 4), device=dev)
+    re = torch.as_tensor(_DeviceWords(re_ptr, 4, "<i4", 4), device=dev)
+    torch.cuda.synchronize(dev)
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(acc)
+        dist.all_reduce(sizes)
+        dist.all_reduce(re)
+        torch.cuda.current_stream(dev).synchronize()
+    return layer.step_finish()

@@ -92,6 +92,20 @@ class Solver:
                    "rbp_solver_step_timed")
         return t.value, a.value, b.value
 
+    def sample(self):
+        """BATCHED fold, first half: sample this rank's trees and reduce them to blocked partial sums (device)."""
+        _ffi.check(self._lib.rbp_solver_sample(self._h), "rbp_solver_sample")
+
+    def delta_buffer(self):
+        """(device pointer, bytes) of this rank's partial sums — what ranks all-gather."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _ffi.check(self._lib.rbp_solver_delta_buffer(self._h, ctypes.byref(p), ctypes.byref(n)), "rbp_solver_delta_buffer")
+        return p.value, n.value
+
+    def fold_gathered(self, dev_ptr, world_size):
+        """BATCHED fold, second half: rank-ordered sum of the gathered partials + one schedule application per row."""
+        _ffi.check(self._lib.rbp_solver_fold_gathered(self._h, ctypes.c_void_p(dev_ptr), world_size), "rbp_solver_fold_gathered")
+
     def solve(self, trees):
         """`Solver::solve(trees)`: trees / batch_size steps (solver.rs:111-122)."""
         return self.step(trees // self.batch)

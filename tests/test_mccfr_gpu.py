@@ -124,3 +124,50 @@ def test_welford_division_is_ieee_exact(rbp):
     bad = ctypes.c_uint64(1)
     st = rbp.load_library().rbp_selftest_div_by_count(1 << 22, 64, ctypes.byref(bad))
     assert st == 0 and bad.value == 0, bad.value
+
+
+BATCHED = [
+    ("kuhn", "FlooredRegret", "LinearWeight", "ExternalSampling", 1, 500),
+    ("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", 1000, 40),
+    ("leduc", "LinearRegret", "QuadraticWeight", "ExternalSampling", 129, 60),
+    ("leduc", "DiscountedRegret", "ExponentialWeight", "PrunableSampling", 300, 50),
+    ("leduc", "SummedRegret", "ConstantWeight", "ExternalSampling", 16384, 5),
+]
+
+
+@pytest.mark.parametrize("game,regret,weight,sampling,batch,epochs", BATCHED)
+def test_batched_fold_bit_exact(rbp, oracle, game, regret, weight, sampling, batch, epochs):
+    g = rbp.Solver(game, regret, weight, sampling, batch=batch, seed=4, fold=rbp.FOLD_BATCHED)
+    o = oracle.OracleSolver(game, regret, weight, sampling, batch=batch, seed=4, threads=4)
+    o.set_fold(1)
+    g.step(epochs)
+    o.step(epochs)
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.counters() == o.counters()
+
+
+def test_batched_two_ranks_on_one_gpu(rbp, oracle):
+    # world_size 2 emulated in one process: two handles own tree ids [0,B) and [B,2B); the exchange is a concat
+    import torch
+
+    from robopoker_b200.distributed import _DeviceWords
+
+    B, E = 640, 20
+    hs = [rbp.Solver("leduc", "LinearRegret", "LinearWeight", batch=B, seed=8, fold=rbp.FOLD_BATCHED) for _ in range(2)]
+    os_ = [oracle.OracleSolver("leduc", "LinearRegret", "LinearWeight", batch=B, seed=8, threads=4) for _ in range(2)]
+    for r in range(2):
+        hs[r].set_world(r, 2)
+        os_[r].set_fold(1, r, 2)
+    views = [torch.as_tensor(_DeviceWords(*h.delta_buffer()), device="cuda") for h in hs]
+    for _ in range(E):
+        for h in hs:
+            h.sample()
+        gathered = torch.cat(views)
+        torch.cuda.synchronize()
+        for h in hs:
+            h.fold_gathered(gathered.data_ptr(), 2)
+        words = np.concatenate([o.sample() for o in os_])
+        for o in os_:
+            o.fold_gathered(words, 2)
+    rows_equal(hs[0].profile_rows(), hs[1].profile_rows())
+    rows_equal(hs[0].profile_rows(), os_[0].profile_rows())
