@@ -29,11 +29,14 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=16384, help="trees per epoch per GPU")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--fold", default="batched", choices=["ordered", "batched"],
+                   help="ordered = reference Solver::step semantics (serial per row); batched = blocked delta sums (scales across GPUs)")
     return p.parse_args()
 
 
 def workload(args, n):
-    return {"workload": f"configs[1] Leduc MCCFR ({REGRET},{WEIGHT},{SAMPLING}), {args.batch} trees/epoch/GPU, ordered fold",
+    return {"workload": f"configs[1] Leduc MCCFR ({REGRET},{WEIGHT},{SAMPLING}), {args.batch} trees/epoch/GPU, {args.fold} fold",
+            "fold": args.fold,
             "game": GAME, "trees_per_epoch_per_gpu": args.batch, "global_batch": args.batch * n, "parallelism": f"trees x{n}",
             "table_rows": 240, "l2": "flushed between steps (192 MiB write), untimed"}
 
@@ -81,6 +84,7 @@ def cpu_baseline_run(args, epochs, threads):
     from oracle import binding as oracle
 
     o = oracle.OracleSolver(GAME, REGRET, WEIGHT, SAMPLING, batch=args.batch, seed=args.seed, threads=threads)
+    o.set_fold(1 if args.fold == "batched" else 0)
     o.step(1)
     u0 = o.counters()["updates"]
     t0 = time.perf_counter()
@@ -97,6 +101,7 @@ def run_reference(args):
     from oracle import binding as oracle
 
     o = oracle.OracleSolver(GAME, REGRET, WEIGHT, SAMPLING, batch=args.batch, seed=args.seed, threads=threads)
+    o.set_fold(1 if args.fold == "batched" else 0)
     o.step(args.warmup)
     u0 = o.counters()["updates"]
     t0 = time.perf_counter()
@@ -135,29 +140,48 @@ def main():
     if l.rbp_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device — librbp_b200 has no CPU fallback")
 
-    s = rbp.Solver(GAME, REGRET, WEIGHT, SAMPLING, batch=args.batch, seed=args.seed, device=local)
-    s.set_world(rank, world)
-    launches0 = l.rbp_kernel_launches()
-    s.step_timed(max(args.warmup, 3), flush_l2=True)
-    u0 = s.counters()["updates"]
-    if dist:
+    fold = rbp.FOLD_BATCHED if args.fold == "batched" else rbp.FOLD_ORDERED
+    if world > 1 and args.fold != "batched":
+        raise SystemExit("bench.py: --gpus > 1 needs --fold batched (the ordered fold is serial per row and does not shard)")
+    s = rbp.Solver(GAME, REGRET, WEIGHT, SAMPLING, batch=args.batch, seed=args.seed, device=local, fold=fold)
+    warm = max(args.warmup, 3)
+    if world == 1:
+        s.step_timed(warm, flush_l2=True)
+        u0 = s.counters()["updates"]
+        clocks = Clocks(local)
+        l0 = l.rbp_kernel_launches()
+        ms_total, ms_sample, ms_fold = s.step_timed(args.steps, flush_l2=True)
+        gpu_launches = l.rbp_kernel_launches() - l0
+        clk = clocks.stop()
+        updates = s.counters()["updates"] - u0
+    else:
         import torch
+        from robopoker_b200.distributed import ShardedSolver
+
+        stream = torch.cuda.current_stream()
+        s.set_stream(stream.cuda_stream)
+        sh = ShardedSolver(s, dist, device=local)
+        flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+        sh.step(warm)
+        u0 = s.counters()["updates"]
         dist.barrier(); torch.cuda.synchronize()
-    clocks = Clocks(local)
-    l0 = l.rbp_kernel_launches()
-    ms_total, ms_sample, ms_fold = s.step_timed(args.steps, flush_l2=True)
-    gpu_launches = l.rbp_kernel_launches() - l0
-    if dist:
-        import torch
-        dist.barrier(); torch.cuda.synchronize()
+        clocks = Clocks(local)
+        l0 = l.rbp_kernel_launches()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            flush.zero_()          # L2 flush, untimed
+            e0.record(stream)
+            sh.step(1)             # sample -> all-gather (NCCL) -> fold, all on this stream
+            e1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        ms_sample = ms_fold = float("nan")
+        gpu_launches = l.rbp_kernel_launches() - l0
+        clk = clocks.stop()
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    clk = clocks.stop()
-    updates = s.counters()["updates"] - u0
-    if dist:
-        import torch
-        t = torch.tensor([updates], device="cuda", dtype=torch.float64)
+        t = torch.tensor([s.counters()["updates"] - u0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         updates = float(t.item())
     value = updates / (ms_total * 1e-3)
@@ -167,18 +191,29 @@ def main():
     buf = np.zeros(len(rows) + 16, dtype=rows.dtype)
     e_steps = max(10, min(args.steps, 200))
     epochs = s.epochs
+    stepper = (lambda: s.step(1)) if world == 1 else (lambda: sh.step(1))
     for _ in range(3):
-        s.import_rows(rows, epochs); s.step(1); rows = s.profile_rows(buf).copy(); epochs += 1
+        s.import_rows(rows, epochs); stepper(); rows = s.profile_rows(buf).copy(); epochs += 1
     ue0 = s.counters()["updates"]
+    if dist:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        s.import_rows(rows, epochs)
-        s.step(1)
-        rows = s.profile_rows(buf)
+        s.import_rows(rows, epochs)   # H2D: the host mirror of the profile (what `MutProf::mut_*` edits)
+        stepper()
+        rows = s.profile_rows(buf)    # D2H: the refreshed host mirror
         epochs += 1
     e_dt = time.perf_counter() - t0
     e_updates = s.counters()["updates"] - ue0
-    e2e_val = e_updates / e_dt * world  # ranks run the same code path concurrently
+    if dist:
+        import torch
+        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.item())
+        t = torch.tensor([e_updates], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        e_updates = float(t.item())
+    e2e_val = e_updates / e_dt
     row_bytes = 24 * len(rows)
 
     # roofline of the dominant kernel (the ordered fold): algorithmic bytes = 32 B per infoset-action update
@@ -190,12 +225,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_launch_updates = updates / world / args.steps
-    fold_s = ms_fold * 1e-3 / args.steps
-    achieved = 32.0 * per_launch_updates / fold_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "mccfr_fold_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    if args.fold == "ordered":
+        dom, dom_s = "mccfr_fold_kernel", ms_fold * 1e-3 / args.steps
+        note = "240-row table is L2-resident; the ordered fold is bound by the reference's serial-per-row schedule, not by HBM"
+    else:
+        dom, dom_s = "mccfr_sample_kernel", (ms_sample if world == 1 else ms_total) * 1e-3 / args.steps
+        note = ("sampling kernel: latency/divergence-bound tree walks over L1/L2-resident tables (SURVEY 8d: reported, not claimed "
+                "against the HBM roofline); algorithmic bytes = 32 B per infoset-action update")
+    achieved = 32.0 * per_launch_updates / dom_s / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured" if peaks else "fallback", "traffic": None,
-                "kernel_ms": {"mccfr_sample_kernel": ms_sample / args.steps, "mccfr_fold_kernel": ms_fold / args.steps},
-                "note": "240-row table is L2-resident; the fold is bound by the reference's ordered (serial-per-row) schedule, not by HBM"}
+                "kernel_ms": {"mccfr_sample_kernel": ms_sample / args.steps, "fold_kernels": ms_fold / args.steps}, "note": note}
 
     if rank == 0:
         threads = os.cpu_count() or 1

@@ -89,6 +89,8 @@ typedef struct rbp_solver rbp_solver_t;
 int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_mode, int batch, uint64_t seed,
                       const rbp_hyper_t* hyper /* NULL = defaults */, int device, rbp_solver_t** out);
 int rbp_solver_set_world(rbp_solver_t* s, int world_rank, int world_size);
+/* run this handle's kernels on a caller-owned cudaStream_t (e.g. the stream a collective library uses) */
+int rbp_solver_set_stream(rbp_solver_t* s, void* cuda_stream);
 void rbp_solver_destroy(rbp_solver_t* s);
 /* `Solver::step` ×n (solver.rs:96-105) — sample `batch` trees, compute Decisions, fold, advance epoch */
 int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs);

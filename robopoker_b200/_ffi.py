@@ -51,6 +51,7 @@ def load_library():
     l.rbp_philox4x32_10.argtypes = [P(u32), P(u32), P(u32)]
     l.rbp_solver_create.argtypes = [i32, i32, i32, i32, i32, i32, u64, P(HyperC), i32, P(vp)]
     l.rbp_solver_set_world.argtypes = [vp, i32, i32]
+    l.rbp_solver_set_stream.argtypes = [vp, vp]
     l.rbp_solver_destroy.argtypes = [vp]
     l.rbp_solver_destroy.restype = None
     l.rbp_solver_step.argtypes = [vp, u64]

@@ -789,6 +789,7 @@ struct rbp_solver {
     std::vector<void*> owned;
     std::vector<uint8_t> touched;  // rows written by import (export lists visits>0 or touched)
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     int device = 0, regret = 0, weight = 0, sampling = 0, fold_mode = 0, batch = 1;
     int world_rank = 0, world_size = 1;
     uint64_t seed = 0, epochs = 0;
@@ -1004,6 +1005,16 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
     return RBP_OK;
 }
 
+int rbp_solver_set_stream(rbp_solver_t* s, void* cuda_stream) {
+    if (!s) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(s->device));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return RBP_OK;
+}
+
 int rbp_solver_set_world(rbp_solver_t* s, int world_rank, int world_size) {
     if (!s || world_size < 1 || world_rank < 0 || world_rank >= world_size) return RBP_ERR_INVALID;
     s->world_rank = world_rank; s->world_size = world_size;
@@ -1013,7 +1024,7 @@ int rbp_solver_set_world(rbp_solver_t* s, int world_rank, int world_size) {
 void rbp_solver_destroy(rbp_solver_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    if (s->stream) { cudaStreamSynchronize(s->stream); if (s->own_stream) cudaStreamDestroy(s->stream); }
     for (void* p : s->owned) cudaFree(p);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     delete s;

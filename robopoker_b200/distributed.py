@@ -15,7 +15,7 @@ import numpy as np
 class _DeviceWords:
     """Zero-copy view of library-owned device memory for torch (`__cuda_array_interface__`)."""
 
-    def __init__(self, ptr, nbytes, typestr="<u4", itemsize=4):
+    def __init__(self, ptr, nbytes, typestr="<i4", itemsize=4):
         self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 

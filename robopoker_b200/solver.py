@@ -80,6 +80,9 @@ class Solver:
     def set_world(self, rank, size):
         _ffi.check(self._lib.rbp_solver_set_world(self._h, rank, size), "rbp_solver_set_world")
 
+    def set_stream(self, cuda_stream):
+        _ffi.check(self._lib.rbp_solver_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "rbp_solver_set_stream")
+
     def step(self, n=1):
         """`Solver::step` × n."""
         _ffi.check(self._lib.rbp_solver_step(self._h, n), "rbp_solver_step")
