@@ -24,10 +24,10 @@ GAME, REGRET, WEIGHT, SAMPLING = "leduc", "FlooredRegret", "LinearWeight", "Exte
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--batch", type=int, default=16384, help="trees per epoch per GPU")
+    p.add_argument("--batch", type=int, default=262144, help="trees per epoch per GPU")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--fold", default="batched", choices=["ordered", "batched"],
                    help="ordered = reference Solver::step semantics (serial per row); batched = blocked delta sums (scales across GPUs)")

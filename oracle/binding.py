@@ -240,3 +240,45 @@ def variation(x, y):
     l.orc_variation.restype = ctypes.c_float
     l.orc_variation.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     return l.orc_variation(x.ctypes.data, y.ctypes.data, len(x))
+
+
+def _sink():
+    l = lib()
+    if not getattr(l, "_sink_ready", False):
+        vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        l.orc_exp_c.restype = f32
+        l.orc_exp_c.argtypes = [f32]
+        l.orc_ln_c.restype = f32
+        l.orc_ln_c.argtypes = [f32]
+        l.orc_ot_cost.restype = f32
+        l.orc_ot_cost.argtypes = [vp, vp, i32, vp, i32, f32, i32, f32, ctypes.POINTER(i32)]
+        l.orc_sinkhorn_divergence_batch.argtypes = [vp, vp, ctypes.c_int64, i32, vp, i32, vp, i32]
+        l._sink_ready = True
+    return l
+
+
+def exp_c(x):
+    return _sink().orc_exp_c(x)
+
+
+def ln_c(x):
+    return _sink().orc_ln_c(x)
+
+
+def ot_cost(mu, nu, tri, math=0, temperature=0.025, iterations=128, tolerance=0.0005):
+    mu = np.ascontiguousarray(mu, dtype=np.uint32)
+    nu = np.ascontiguousarray(nu, dtype=np.uint32)
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    it = ctypes.c_int()
+    c = _sink().orc_ot_cost(mu.ctypes.data, nu.ctypes.data, len(mu), tri.ctypes.data, math, temperature, iterations, tolerance, ctypes.byref(it))
+    return c, it.value
+
+
+def sinkhorn_divergence_batch(a, b, tri, math=0, threads=8):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    n, bins = a.shape
+    out = np.zeros(n, np.float32)
+    _sink().orc_sinkhorn_divergence_batch(a.ctypes.data, b.ctypes.data, n, bins, tri.ctypes.data, math, out.ctypes.data, threads)
+    return out

@@ -589,27 +589,33 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
 }
 
 // ───────────────────────────── K3b: BATCHED fold ─────────────────────────────
-// rank level of the blocked order: one warp per infoset, lane f sums field f over this rank's tree-blocks in order
-__global__ void __launch_bounds__(32)
+// rank level of the blocked order: one block per infoset, warp f sums field f over this rank's tree-blocks in
+// order.  Lanes fetch 32 consecutive block partials with one coalesced load; the sum itself stays sequential
+// (shuffle-fed), because the blocked order is part of the contract.
+constexpr int kPartialFields = 2 * kMaxActions + 2;  // dr[4], pay, na[4], n
+__global__ void __launch_bounds__(32 * kPartialFields)
 mccfr_rank_partial_kernel(DevGame g, Scratch sc, Partial* __restrict__ out) {
-    const int x = blockIdx.x, lane = threadIdx.x, I = g.n_infos;
-    if (lane < kMaxActions + 1) {
-        const float* src = sc.bp_f + ((size_t)lane * I + x) * sc.nblk;
+    const int x = blockIdx.x, lane = threadIdx.x & 31, f = threadIdx.x >> 5, I = g.n_infos;
+    if (f < kMaxActions + 1) {
+        const float* src = sc.bp_f + ((size_t)f * I + x) * sc.nblk;
         float acc = 0.0f;
-        for (int b = 0; b < sc.nblk; ++b) acc = acc + src[b];
-        if (lane < kMaxActions) out[x].dr[lane] = acc; else out[x].pay = acc;
-    } else if (lane < 2 * kMaxActions + 1) {
-        const int a = lane - (kMaxActions + 1);
-        const uint32_t* src = sc.bp_na + ((size_t)a * I + x) * sc.nblk;
+        for (int b0 = 0; b0 < sc.nblk; b0 += 32) {
+            const float v = b0 + lane < sc.nblk ? src[b0 + lane] : 0.0f;
+            const int m = min(32, sc.nblk - b0);
+            for (int k = 0; k < m; ++k) acc = acc + __shfl_sync(0xFFFFFFFFu, v, k);
+        }
+        if (lane == 0) { if (f < kMaxActions) out[x].dr[f] = acc; else out[x].pay = acc; }
+    } else {
+        const bool is_n = f == 2 * kMaxActions + 1;
+        const uint32_t* src = is_n ? reinterpret_cast<const uint32_t*>(sc.m_cnt + (size_t)x * sc.nblk)
+                                   : sc.bp_na + ((size_t)(f - kMaxActions - 1) * I + x) * sc.nblk;
         uint32_t acc = 0;
-        for (int b = 0; b < sc.nblk; ++b) acc += src[b];
-        out[x].na[a] = acc;
-    } else if (lane == 2 * kMaxActions + 1) {
-        const int32_t* src = sc.m_cnt + (size_t)x * sc.nblk;
-        uint32_t acc = 0;
-        for (int b = 0; b < sc.nblk; ++b) acc += (uint32_t)src[b];
-        out[x].n = acc;
-        out[x].pad[0] = out[x].pad[1] = 0u;
+        for (int b = lane; b < sc.nblk; b += 32) acc += src[b];
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+        if (lane == 0) {
+            if (is_n) { out[x].n = acc; out[x].pad[0] = out[x].pad[1] = 0u; }
+            else out[x].na[f - kMaxActions - 1] = acc;
+        }
     }
 }
 __device__ __forceinline__ float regret_gain_rt(const EpochArgs& ep, float net, float add) {
@@ -840,7 +846,7 @@ int launch_sample(rbp_solver* s, const EpochArgs& ep) {
     return RBP_OK;
 }
 int launch_rank_partial(rbp_solver* s) {
-    mccfr_rank_partial_kernel<<<s->dev.n_infos, 32, 0, s->stream>>>(s->dev, s->sc, s->delta);
+    mccfr_rank_partial_kernel<<<s->dev.n_infos, 32 * kPartialFields, 0, s->stream>>>(s->dev, s->sc, s->delta);
     RBP_LAUNCHED();
     return RBP_OK;
 }
