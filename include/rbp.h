@@ -148,7 +148,10 @@ int rbp_river_equity_device(const uint64_t* d_pocket, const uint64_t* d_public, 
 /* ─────────────────────────────── lloyd / elkan: k-means abstraction layers ─────────────────────────────── */
 
 /* distance kinds of `Metric::emd` (crates/lloyd/src/metric.rs:109-115) */
-enum { RBP_KMEANS_W1 = 0 /* Equity::variation over the 101 river-equity buckets (turn layer) */ };
+enum {
+    RBP_KMEANS_W1 = 0,      /* Equity::variation over the 101 river-equity buckets (turn layer) */
+    RBP_KMEANS_SINKHORN = 1 /* Sinkhorn::divergence over next-street clusters with a ground metric (flop layer) */
+};
 
 typedef struct rbp_kmeans rbp_kmeans_t;
 
@@ -157,6 +160,10 @@ typedef struct rbp_kmeans rbp_kmeans_t;
  * The points are copied to the device once and stay resident. */
 int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out);
 void rbp_kmeans_destroy(rbp_kmeans_t* h);
+/* SINKHORN layers only: the ground `Metric` of the next street (crates/lloyd/src/metric.rs:25-31; `Layer::build`
+ * loads it with `Metric::from_street`, layer.rs:262): tri[bins(bins-1)/2] in `Pair::merge` order, diagonal implied 0.
+ * Must be set before centroids; also computes the memoised self terms OT(x,x) of every point (sinkhorn.rs:172-191). */
+int rbp_kmeans_set_metric(rbp_kmeans_t* h, const float* tri, int bins);
 /* `Layer::init_centroids` k-means++ (layer.rs:140-181).  The reference's SmallRng/WeightedIndex<f32> stream is
  * replaced by the integer-weight contract: round r draws word = Philox(counter=(r,0,0,3), key=seed),
  * q_i = (u64)(min(potential_i, 2^20) * 2^32), T = Σ q_i, x = mulhi64(word, T), pick = first i with x < Σ_{k<=i} q_k.
@@ -188,6 +195,16 @@ int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out);
 int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out);
 /* CUDA-event timing on the library stream: what = 0 full step, 1 N x K assignment sweep */
 int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out);
+
+/* `Metric::emd` / `Sinkhorn::divergence` (crates/lloyd/src/metric.rs:109-115, sinkhorn.rs:166-171) for explicit pairs:
+ * out[t] = max(0, OT(A[ia[t]], B[ib[t]]) - OT(A,A)/2 - OT(B,B)/2) over dense u32 histograms a_counts[na][bins],
+ * b_counts[nb][bins].  Log-domain Sinkhorn exactly as sinkhorn.rs:77-139 (defaults T=0.025, 128 iterations, tol 5e-4,
+ * hyperparams/sinkhorn.rs:17-23), sequential sums in ascending-bucket order.  exp/ln contract (replaces the platform
+ * libm of `f32::exp`/`f32::ln`, which no reference test pins): exp_c = 2^k * P5(r), k = rint(x*log2e),
+ * r = x - k*ln2 (0.693359375, -2.12194440e-4 split, fma), Cephes coefficients; ln_c = Cephes logf on m in
+ * [sqrt(1/2), sqrt 2); both as fixed IEEE operation sequences without contraction. */
+int rbp_sinkhorn_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb, int bins, const int32_t* ia, const int32_t* ib,
+                       int64_t n, const float* tri, float temperature, int iterations, float tolerance, float* out);
 
 #ifdef __cplusplus
 }

@@ -169,6 +169,7 @@ class OracleKmeans:
             l.orc_kmeans_create.restype = vp
             l.orc_kmeans_create.argtypes = [vp, i32, i32, i32, i32]
             l.orc_kmeans_destroy.argtypes = [vp]
+            l.orc_kmeans_set_metric.argtypes = [vp, vp]
             l.orc_kmeans_init_pp.argtypes = [vp, ctypes.c_uint64, vp]
             l.orc_kmeans_set_centroids_from_points.argtypes = [vp, vp]
             l.orc_kmeans_init_bounds.argtypes = [vp]
@@ -189,6 +190,11 @@ class OracleKmeans:
         if getattr(self, "_h", None):
             self._l.orc_kmeans_destroy(self._h)
             self._h = None
+
+    def set_metric(self, tri):
+        tri = np.ascontiguousarray(tri, dtype=np.float32)
+        assert len(tri) == self.bins * (self.bins - 1) // 2
+        self._l.orc_kmeans_set_metric(self._h, tri.ctypes.data)
 
     def init_centroids(self, seed=0):
         chosen = np.zeros(self.k, np.int32)

@@ -21,12 +21,20 @@ Kmeans* orc_kmeans_create(const uint8_t* counts, int n, int bins, int k, int thr
     return m;
 }
 void orc_kmeans_destroy(Kmeans* m) { delete m; }
+// flop layer: switch to Sinkhorn divergence under the ground metric `tri` (Pair::merge order)
+void orc_kmeans_set_metric(Kmeans* m, const float* tri) {
+    m->kind = 1;
+    m->ground.bins = m->B;
+    m->ground.tri.assign(tri, tri + (size_t)m->B * (m->B - 1) / 2);
+    m->build_point_measures();
+}
 void orc_kmeans_init_pp(Kmeans* m, uint64_t seed, int* chosen) {
     std::vector<int> c = m->init_plusplus(seed);
     if (chosen) std::memcpy(chosen, c.data(), c.size() * sizeof(int));
 }
 void orc_kmeans_set_centroids_from_points(Kmeans* m, const int* idx) {
     for (int j = 0; j < m->K; ++j) m->set_centroid_from_point(j, idx[j]);
+    if (m->kind == 1) Kmeans::centroid_measures(*m, m->ccounts, m->cmeas, m->cself);
 }
 void orc_kmeans_init_bounds(Kmeans* m) { m->init_bounds(); }
 void orc_kmeans_step(Kmeans* m, float* drift, uint32_t* sizes, uint32_t* reassigned) {

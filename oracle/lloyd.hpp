@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "rng.hpp"
+#include "sinkhorn.hpp"
 
 namespace orc {
 
@@ -43,6 +44,32 @@ struct Kmeans {
     std::vector<uint32_t> prior;      // assignments before the step (Prior::tally)
     int threads = 1;
     uint64_t dist_evals = 0;
+    // kind 0: W1 `Equity::variation` (turn layer);  kind 1: `Sinkhorn::divergence` under a ground metric (flop layer,
+    // metric.rs:109-115).  For kind 1 the self terms OT(h,h) are memoised per histogram as the reference does
+    // (sinkhorn.rs:172-191) and argument order is preserved (the divergence is not symmetric in f32).
+    int kind = 0;
+    GroundMetric ground;
+    SinkhornParams hp;
+    std::vector<Measure> pmeas, cmeas;
+    std::vector<float> pself, cself;
+
+    void build_point_measures() {
+        pmeas.resize(N); pself.resize(N);
+        parallel(N, [&](int i) {
+            pmeas[i] = Measure::from_counts(&points[(size_t)i * B], B);
+            pself[i] = ot_cost<Math::Contract>(pmeas[i], pmeas[i], ground, hp);
+        });
+    }
+    static void centroid_measures(const Kmeans& km, const std::vector<uint64_t>& counts, std::vector<Measure>& meas, std::vector<float>& self) {
+        meas.resize(km.K); self.resize(km.K);
+        km.parallel(km.K, [&](int j) {
+            meas[j] = Measure::from_counts(&counts[(size_t)j * km.B], km.B);
+            self[j] = meas[j].idx.empty() ? 0.0f : ot_cost<Math::Contract>(meas[j], meas[j], km.ground, km.hp);
+        });
+    }
+    float sk(const Measure& a, float sa, const Measure& b, float sb) const {
+        return divergence_from(ot_cost<Math::Contract>(a, b, ground, hp), sa, sb);
+    }
 
     // bins.rs:58-60
     static inline float dens(uint64_t count, uint64_t weight) { return (float)count / (float)weight; }
@@ -57,10 +84,22 @@ struct Kmeans {
         }
         return acc / (float)B;
     }
+    float d_pc(int i, int j) const {  // distance(x_i, c_j): refresh / rebound (elkan.rs:113-123)
+        if (kind == 1) return sk(pmeas[i], pself[i], cmeas[j], cself[j]);
+        return d_point_centroid(i, j);
+    }
+    float d_cp(int j, int i) const {  // distance(c_j, x_i): neighbor (elkan.rs:68-77)
+        if (kind == 1) return sk(cmeas[j], cself[j], pmeas[i], pself[i]);
+        return d_point_centroid(i, j);
+    }
     float d_point_centroid(int i, int j) const {
         const uint8_t* p = &points[(size_t)i * B];
         const uint64_t* c = &ccounts[(size_t)j * B];
         return variation([&](int b) { return (uint64_t)p[b]; }, pweight[i], [&](int b) { return c[b]; }, cweight[j]);
+    }
+    float d_pp(int i, int k) const {  // distance(x_i, x_k): k-means++ (layer.rs:171)
+        if (kind == 1) return sk(pmeas[i], pself[i], pmeas[k], pself[k]);
+        return d_point_point(i, k);
     }
     float d_point_point(int i, int k) const {
         const uint8_t* p = &points[(size_t)i * B];
@@ -110,21 +149,22 @@ struct Kmeans {
             set_centroid_from_point(r, pick);
             pot[pick] = 0.0f;
             parallel(N, [&](int i) {
-                float d = d_point_point(pick, i);  // distance(&x, h)
+                float d = d_pp(pick, i);  // distance(&x, h)
                 float d2 = d * d;
                 pot[i] = d2 < pot[i] ? d2 : pot[i];  // Energy::min(d0, d1)
             });
             dist_evals += N;
         }
+        if (kind == 1) centroid_measures(*this, ccounts, cmeas, cself);
         return chosen;
     }
 
     // elkan.rs:68-77 neighbor: argmin_j distance(c_j, x), first minimum (Iterator::min_by)
     void neighbor(int i, uint32_t* j_out, float* d_out) const {
         int best = 0;
-        float bd = d_point_centroid(i, 0);  // variation is exactly symmetric in its arguments
+        float bd = d_cp(0, i);
         for (int j = 1; j < K; ++j) {
-            float d = d_point_centroid(i, j);
+            float d = d_cp(j, i);
             if (d < bd) { bd = d; best = j; }
         }
         *j_out = (uint32_t)best;
@@ -145,7 +185,9 @@ struct Kmeans {
         std::vector<float> pair((size_t)K * K, 0.0f), mid(K, FLT_MAX);
         parallel(K, [&](int i) {  // elkan.rs:80-93 pairwises (both triangles computed)
             for (int j = 0; j < K; ++j)
-                pair[(size_t)i * K + j] = i == j ? 0.0f : d_centroids(&ccounts[(size_t)i * B], cweight[i], &ccounts[(size_t)j * B], cweight[j]);
+                pair[(size_t)i * K + j] = i == j ? 0.0f
+                    : (kind == 1 ? sk(cmeas[i], cself[i], cmeas[j], cself[j])
+                                 : d_centroids(&ccounts[(size_t)i * B], cweight[i], &ccounts[(size_t)j * B], cweight[j]));
         });
         for (int i = 0; i < K; ++i)  // elkan.rs:95-105 midpoints
             for (int j = 0; j < K; ++j)
@@ -155,13 +197,13 @@ struct Kmeans {
             if (!(upper[i] > mid[assign[i]])) return;  // filter(|b| b.u() > midpoints[b.j()])
             float* l = &lower[(size_t)i * K];
             if (stale[i]) {  // elkan.rs:113-117 + bounds.rs:76-80 refresh
-                float d = d_point_centroid(i, (int)assign[i]);
+                float d = d_pc(i, (int)assign[i]);
                 l[assign[i]] = d; upper[i] = d; stale[i] = 0;
             }
             for (int j = 0; j < K; ++j) {  // elkan.rs:118-123 rebound
                 uint32_t c = assign[i];
                 if ((int)c != j && upper[i] > l[j] && upper[i] > 0.5f * pair[(size_t)c * K + j]) {  // bounds.rs:57-61
-                    float d = d_point_centroid(i, j);
+                    float d = d_pc(i, j);
                     l[j] = d;  // bounds.rs:81-87 witness
                     if (d < upper[i]) { assign[i] = (uint32_t)j; upper[i] = d; }
                 }
@@ -176,8 +218,12 @@ struct Kmeans {
         }
         StepOut out;
         out.drift.resize(K);
+        std::vector<Measure> nmeas;
+        std::vector<float> nself;
+        if (kind == 1) centroid_measures(*this, nc, nmeas, nself);
         for (int j = 0; j < K; ++j)  // elkan.rs:107-109 drift = distance(new, old)
-            out.drift[j] = d_centroids(&nc[(size_t)j * B], nw[j], &ccounts[(size_t)j * B], cweight[j]);
+            out.drift[j] = kind == 1 ? sk(nmeas[j], nself[j], cmeas[j], cself[j])
+                                     : d_centroids(&nc[(size_t)j * B], nw[j], &ccounts[(size_t)j * B], cweight[j]);
         parallel(N, [&](int i) {  // bounds.rs:65-74 update
             float* l = &lower[(size_t)i * K];
             for (int j = 0; j < K; ++j) { float v = l[j] - out.drift[j]; l[j] = v > 0.0f ? v : 0.0f; }
@@ -185,6 +231,7 @@ struct Kmeans {
             stale[i] = 1;
         });
         ccounts.swap(nc); cweight.swap(nw);
+        if (kind == 1) { cmeas.swap(nmeas); cself.swap(nself); }
         out.sizes.assign(K, 0);
         out.reassigned = 0;
         for (int i = 0; i < N; ++i) { out.sizes[assign[i]]++; out.reassigned += assign[i] != prior[i]; }  // elkan/src/prior.rs:35-47
@@ -197,8 +244,10 @@ struct Kmeans {
         float mx = FLT_MIN;
         for (int i = 0; i < K; ++i)
             for (int j = 0; j < i; ++j) {
-                float a = d_centroids(&ccounts[(size_t)i * B], cweight[i], &ccounts[(size_t)j * B], cweight[j]);
-                float b = d_centroids(&ccounts[(size_t)j * B], cweight[j], &ccounts[(size_t)i * B], cweight[i]);
+                float a = kind == 1 ? sk(cmeas[i], cself[i], cmeas[j], cself[j])
+                                    : d_centroids(&ccounts[(size_t)i * B], cweight[i], &ccounts[(size_t)j * B], cweight[j]);
+                float b = kind == 1 ? sk(cmeas[j], cself[j], cmeas[i], cself[i])
+                                    : d_centroids(&ccounts[(size_t)j * B], cweight[j], &ccounts[(size_t)i * B], cweight[i]);
                 float d = (a + b) / 2.0f;
                 tri[(size_t)i * (i - 1) / 2 + j] = d;
                 mx = d > mx ? d : mx;  // fold(f32::MIN_POSITIVE, f32::max)

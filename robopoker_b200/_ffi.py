@@ -90,6 +90,8 @@ def load_library():
     l.rbp_kmeans_metric.argtypes = [vp, vp]
     l.rbp_kmeans_bounds.argtypes = [vp, vp, vp, vp, vp]
     l.rbp_kmeans_timed.argtypes = [vp, i32, i32, f32p]
+    l.rbp_kmeans_set_metric.argtypes = [vp, vp, i32]
+    l.rbp_sinkhorn_batch.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp, ctypes.c_float, i32, ctypes.c_float, vp]
     _lib = l
     return l
 

@@ -23,6 +23,8 @@ SOURCES = {
     "mccfr.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
     "deuce.cu": ["-fmad=false"],
     "lloyd_w1.cu": ["-fmad=false"],
+    "lloyd_sk.cu": ["-fmad=false"],
+    "kmeans_api.cu": ["-fmad=false"],
 }
 
 

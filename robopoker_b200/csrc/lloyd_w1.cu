@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kmeans_common.cuh"
 
 namespace rbp {
 
@@ -356,10 +357,6 @@ accumulate_kernel(KmDev km, int64_t per_block) {
 }
 
 // ── k-means++ (layer.rs:160-180) under the integer-weight contract of include/rbp.h ──
-__device__ __forceinline__ unsigned long long quantize_potential(float p) {
-    const float q = p < 1048576.0f ? p : 1048576.0f;
-    return (unsigned long long)((double)q * 4294967296.0);
-}
 // potentials update against the newly chosen point + per-block integer sums for the next draw
 __global__ void __launch_bounds__(kThreads)
 pp_update_kernel(KmDev km, float* __restrict__ pot, const int64_t* __restrict__ pick, int first, unsigned long long* __restrict__ bsum) {
@@ -404,54 +401,6 @@ pp_update_kernel(KmDev km, float* __restrict__ pot, const int64_t* __restrict__ 
         bsum[blockIdx.x] = t;
     }
 }
-// draw: x = mulhi64(word, T); pick = first i with x < Σ_{k<=i} q_k   (one block)
-__global__ void __launch_bounds__(1024)
-pp_pick_kernel(KmDev km, const float* __restrict__ pot, const unsigned long long* __restrict__ bsum, int nb, uint32_t w0, uint32_t w1,
-               int64_t* __restrict__ pick, int round, int32_t* __restrict__ chosen) {
-    __shared__ unsigned long long s_part[1024];
-    __shared__ unsigned long long s_x, s_base;
-    __shared__ int s_blk;
-    __shared__ bool s_zero;
-    const int tid = threadIdx.x;
-    // each thread owns a contiguous range of blocks
-    const int per = (nb + 1023) / 1024;
-    const int lo = min(nb, tid * per), hi = min(nb, lo + per);
-    unsigned long long mine = 0;
-    for (int b = lo; b < hi; ++b) mine += bsum[b];
-    s_part[tid] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long T = 0;
-        for (int t = 0; t < 1024; ++t) T += s_part[t];
-        const unsigned long long word = (unsigned long long)w0 << 32 | w1;
-        const unsigned long long x = __umul64hi(word, T);
-        s_x = x;
-        s_zero = T == 0ull;
-        unsigned long long cum = 0;
-        int owner = 1023;
-        for (int t = 0; t < 1024; ++t) { if (x < cum + s_part[t]) { owner = t; break; } cum += s_part[t]; }
-        // inside the owner's block range
-        const int olo = min(nb, owner * per), ohi = min(nb, olo + per);
-        int blk = ohi - 1;
-        for (int b = olo; b < ohi; ++b) { if (x < cum + bsum[b]) { blk = b; break; } cum += bsum[b]; }
-        s_blk = blk < 0 ? 0 : blk;
-        s_base = cum;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const int64_t start = (int64_t)s_blk * kThreads;
-        const int64_t end = min(km.n, start + kThreads);
-        unsigned long long cum = s_base;
-        int64_t p = end - 1;
-        for (int64_t i = start; i < end; ++i) {
-            cum += quantize_potential(pot[i]);
-            if (s_x < cum) { p = i; break; }
-        }
-        if (s_zero) p = km.n - 1;
-        *pick = p;
-        chosen[round] = (int32_t)p;
-    }
-}
 // centroid j := point `pick` (counts + weight)
 __global__ void set_centroid_kernel(KmDev km, const int64_t* __restrict__ pick, int j) {
     const int b = threadIdx.x;
@@ -482,7 +431,12 @@ __global__ void materialize_kernel(KmDev km) {
 
 using namespace rbp;
 
-struct rbp_kmeans {
+struct KmW1;
+namespace rbp {
+void w1_destroy(KmW1* h);
+}
+
+struct KmW1 : rbp_kmeans {
     KmDev d{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -503,7 +457,7 @@ struct rbp_kmeans {
 
 namespace {
 template <class T>
-int kalloc(rbp_kmeans* h, size_t n, T** out) {
+int kalloc(KmW1* h, size_t n, T** out) {
     void* p = nullptr;
     RBP_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
     h->owned.push_back(p);
@@ -511,16 +465,16 @@ int kalloc(rbp_kmeans* h, size_t n, T** out) {
     *out = static_cast<T*>(p);
     return RBP_OK;
 }
-int refresh_centroid_tables(rbp_kmeans* h) {  // CDFs of the current centroids
+int refresh_centroid_tables(KmW1* h) {  // CDFs of the current centroids
     centroid_cdf_kernel<<<(h->d.k + 127) / 128, 128, 0, h->stream>>>(h->d.ccount, h->d.k, h->d.cdf);
     RBP_LAUNCHED();
     return RBP_OK;
 }
 }  // namespace
 
-extern "C" {
+namespace rbp {
 
-int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out) {
+int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out) {
     if (!out) return RBP_ERR_INVALID;
     *out = nullptr;
     if (kind != RBP_KMEANS_W1 || bins != kBins || n < 1 || k < 1 || k > n || !counts) {
@@ -528,9 +482,10 @@ int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* count
         return RBP_ERR_INVALID;
     }
     if (rbp_device_count() <= device) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
-    rbp_kmeans* h = new rbp_kmeans();
+    KmW1* h = new KmW1();
+    h->kind = RBP_KMEANS_W1;
     h->device = device;
-    auto fail = [&](int code) { rbp_kmeans_destroy(h); return code; };
+    auto fail = [&](int code) { w1_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RBP_ERR_CUDA);
     KmDev& d = h->d;
@@ -573,7 +528,7 @@ int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* count
     return RBP_OK;
 }
 
-void rbp_kmeans_destroy(rbp_kmeans_t* h) {
+void w1_destroy(KmW1* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
@@ -581,14 +536,14 @@ void rbp_kmeans_destroy(rbp_kmeans_t* h) {
     delete h;
 }
 
-int rbp_kmeans_init_pp(rbp_kmeans_t* h, uint64_t seed, int32_t* chosen_out) {
+int w1_init_pp(KmW1* h, uint64_t seed, int32_t* chosen_out) {
     if (!h) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     for (int r = 0; r < h->d.k; ++r) {
         pp_update_kernel<<<h->nb, kThreads, 0, h->stream>>>(h->d, h->pot, h->pick, r == 0, h->bsum);
         RBP_LAUNCHED();
         Philox4 w = philox4x32_10((uint32_t)r, 0u, 0u, TAG_KMEANSPP, (uint32_t)seed, (uint32_t)(seed >> 32));
-        pp_pick_kernel<<<1, 1024, 0, h->stream>>>(h->d, h->pot, h->bsum, h->nb, w.r[0], w.r[1], h->pick, r, h->chosen);
+        pp_pick_kernel<<<1, 1024, 0, h->stream>>>(h->d.n, kThreads, h->pot, h->bsum, h->nb, w.r[0], w.r[1], h->pick, r, h->chosen);
         RBP_LAUNCHED();
         set_centroid_kernel<<<1, 128, 0, h->stream>>>(h->d, h->pick, r);
         RBP_LAUNCHED();
@@ -602,7 +557,7 @@ int rbp_kmeans_init_pp(rbp_kmeans_t* h, uint64_t seed, int32_t* chosen_out) {
     return RBP_OK;
 }
 
-int rbp_kmeans_set_centroids(rbp_kmeans_t* h, const uint64_t* counts) {
+int w1_set_centroids(KmW1* h, const uint64_t* counts) {
     if (!h || !counts) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     std::vector<unsigned long long> host((size_t)h->d.k * (kBins + 1));
@@ -619,7 +574,7 @@ int rbp_kmeans_set_centroids(rbp_kmeans_t* h, const uint64_t* counts) {
     return RBP_OK;
 }
 
-int rbp_kmeans_init_bounds(rbp_kmeans_t* h) {
+int w1_init_bounds(KmW1* h) {
     if (!h) return RBP_ERR_INVALID;
     if (!h->have_centroids) { set_last_error("init_bounds before centroids"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
@@ -633,7 +588,7 @@ int rbp_kmeans_init_bounds(rbp_kmeans_t* h) {
 }
 
 // point side of a step + local integer accumulation; multi-GPU hosts all-reduce the accumulator in between
-int rbp_kmeans_step_local(rbp_kmeans_t* h) {
+int w1_step_local(KmW1* h) {
     if (!h) return RBP_ERR_INVALID;
     if (!h->have_bounds) { set_last_error("step before init_bounds"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
@@ -655,21 +610,21 @@ int rbp_kmeans_step_local(rbp_kmeans_t* h) {
     }
     return RBP_OK;
 }
-int rbp_kmeans_accumulator(rbp_kmeans_t* h, void** dev_ptr, size_t* bytes) {
+int w1_accumulator(KmW1* h, void** dev_ptr, size_t* bytes) {
     if (!h || !dev_ptr || !bytes) return RBP_ERR_INVALID;
     *dev_ptr = h->d.acc;
     *bytes = (size_t)h->d.k * (kBins + 1) * sizeof(unsigned long long);
     return RBP_OK;
 }
-int rbp_kmeans_counters(rbp_kmeans_t* h, void** dev_sizes, void** dev_reassigned) {
+int w1_counters(KmW1* h, void** dev_sizes, void** dev_reassigned) {
     if (!h) return RBP_ERR_INVALID;
     if (dev_sizes) *dev_sizes = h->d.sizes;
     if (dev_reassigned) *dev_reassigned = h->d.reassigned;
     return RBP_OK;
 }
-void* rbp_kmeans_stream(rbp_kmeans_t* h) { return h ? (void*)h->stream : nullptr; }
+void* w1_stream(KmW1* h) { return h ? (void*)h->stream : nullptr; }
 
-int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
+int w1_step_finish(KmW1* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
     if (!h) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     KmDev& d = h->d;
@@ -687,13 +642,13 @@ int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_ou
     return RBP_OK;
 }
 
-int rbp_kmeans_step(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
-    int st = rbp_kmeans_step_local(h);
+int w1_step(KmW1* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out) {
+    int st = w1_step_local(h);
     if (st) return st;
-    return rbp_kmeans_step_finish(h, drift_out, sizes_out, reassigned_out);
+    return w1_step_finish(h, drift_out, sizes_out, reassigned_out);
 }
 
-int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* assign_out, float* dist_out) {
+int w1_assign(KmW1* h, uint32_t* assign_out, float* dist_out) {
     if (!h || !assign_out) return RBP_ERR_INVALID;
     if (!h->have_centroids) { set_last_error("assign before centroids"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
@@ -706,7 +661,7 @@ int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* assign_out, float* dist_out) {
     return RBP_OK;
 }
 
-int rbp_kmeans_centroids(rbp_kmeans_t* h, uint64_t* counts_out, uint64_t* weights_out) {
+int w1_centroids(KmW1* h, uint64_t* counts_out, uint64_t* weights_out) {
     if (!h) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     std::vector<unsigned long long> host((size_t)h->d.k * (kBins + 1));
@@ -719,7 +674,7 @@ int rbp_kmeans_centroids(rbp_kmeans_t* h, uint64_t* counts_out, uint64_t* weight
     return RBP_OK;
 }
 
-int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out) {
+int w1_metric(KmW1* h, float* tri_out) {
     if (!h || !tri_out) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     const int total = h->d.k * (h->d.k - 1) / 2;
@@ -733,7 +688,7 @@ int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out) {
     return RBP_OK;
 }
 
-int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out) {
+int w1_bounds(KmW1* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out) {
     if (!h) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     KmDev& d = h->d;
@@ -756,7 +711,7 @@ int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, f
     return RBP_OK;
 }
 
-int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out) {
+int w1_timed(KmW1* h, int what, int iters, float* ms_out) {
     // what: 0 = full step, 1 = assign (N x K distances), device time by CUDA events on the library stream
     if (!h || !ms_out || iters < 1) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
@@ -766,7 +721,7 @@ int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out) {
     RBP_CUDA(cudaEventRecord(e0, h->stream));
     for (int it = 0; it < iters; ++it) {
         int st;
-        if (what == 0) st = rbp_kmeans_step(h, nullptr, nullptr, nullptr);
+        if (what == 0) st = w1_step(h, nullptr, nullptr, nullptr);
         else {
             assign_kernel<false><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
             g_launches.fetch_add(1);
@@ -782,4 +737,4 @@ int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out) {
     return RBP_OK;
 }
 
-}  // extern "C"
+}  // namespace rbp

@@ -8,14 +8,16 @@ import numpy as np
 
 from . import _ffi
 
-KMEANS_W1 = 0
+KMEANS_W1, KMEANS_SINKHORN = 0, 1
 Step = namedtuple("Step", "index drift sizes reassignment")  # crates/elkan/src/step.rs
 
 
 class Layer:
     """Turn-layer clustering: points are histograms over the 101 river-equity buckets, distance `Equity::variation`."""
 
-    def __init__(self, counts, k, device=0):
+    def __init__(self, counts, k, device=0, metric=None):
+        """`metric=None`: turn layer (W1 over 101 river-equity buckets).  `metric=tri`: flop-style layer — points are
+        histograms over next-street clusters compared by `Sinkhorn::divergence` under the triangular ground metric."""
         counts = np.ascontiguousarray(counts, dtype=np.uint8)
         assert counts.ndim == 2
         self.n, self.bins = counts.shape
@@ -23,8 +25,13 @@ class Layer:
         self._lib = _ffi.lib()
         self._h = ctypes.c_void_p()
         self.index = 0
-        _ffi.check(self._lib.rbp_kmeans_create(KMEANS_W1, self.n, self.k, self.bins, counts.ctypes.data, device, ctypes.byref(self._h)),
+        kind = KMEANS_W1 if metric is None else KMEANS_SINKHORN
+        _ffi.check(self._lib.rbp_kmeans_create(kind, self.n, self.k, self.bins, counts.ctypes.data, device, ctypes.byref(self._h)),
                    "rbp_kmeans_create")
+        if metric is not None:
+            tri = np.ascontiguousarray(metric, dtype=np.float32)
+            assert len(tri) == self.bins * (self.bins - 1) // 2
+            _ffi.check(self._lib.rbp_kmeans_set_metric(self._h, tri.ctypes.data, self.bins), "rbp_kmeans_set_metric")
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -117,3 +124,16 @@ class Layer:
         self.init_bounds()
         steps = [self.step() for _ in range(iterations)]
         return self.lookup(), self.metric(), self.future(), steps
+
+
+def sinkhorn_divergence(a_counts, b_counts, ia, ib, tri, temperature=0.025, iterations=128, tolerance=0.0005):
+    """Batched `Metric::emd` → `Sinkhorn::divergence` (crates/lloyd/src/metric.rs:109-115): out[t] = divergence(A[ia[t]], B[ib[t]])."""
+    a = np.ascontiguousarray(a_counts, dtype=np.uint32)
+    b = np.ascontiguousarray(b_counts, dtype=np.uint32)
+    ia = np.ascontiguousarray(ia, dtype=np.int32)
+    ib = np.ascontiguousarray(ib, dtype=np.int32)
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(len(ia), np.float32)
+    _ffi.check(_ffi.lib().rbp_sinkhorn_batch(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], a.shape[1], ia.ctypes.data, ib.ctypes.data,
+                                             len(ia), tri.ctypes.data, temperature, iterations, tolerance, out.ctypes.data), "rbp_sinkhorn_batch")
+    return out

@@ -11,3 +11,20 @@ def turn_histograms(n, seed=0, draws=46, spread=12.0):
     rows = np.repeat(np.arange(n), draws)
     np.add.at(pts, (rows, vals.ravel()), 1)
     return pts
+
+
+def synthetic_metric(bins, seed=0):
+    """Random symmetric ground metric in (0, 1], normalised by its max (SURVEY §8d config 3), triangular Pair::merge order."""
+    rng = np.random.default_rng(seed)
+    tri = rng.uniform(0.05, 1.0, size=bins * (bins - 1) // 2).astype(np.float32)
+    return tri / tri.max()
+
+
+def flop_histograms(n, bins, seed=0, draws=47, spread=3.0):
+    """Synthetic flop-layer points: 47 draws over `bins` next-street clusters, concentrated around a random centre."""
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(0, bins - 1, size=n)
+    vals = np.clip(np.rint(rng.normal(centers[:, None], spread, size=(n, draws))), 0, bins - 1).astype(np.int64)
+    pts = np.zeros((n, bins), dtype=np.uint8)
+    np.add.at(pts, (np.repeat(np.arange(n), draws), vals.ravel()), 1)
+    return pts

@@ -1,0 +1,67 @@
+"""GPU parity for the Sinkhorn path (flop layer): batched divergences and the full Elkan k-means, bit-exact against
+the oracle under the shared exp/ln contract; plus the reference's own property tests on the device."""
+import numpy as np
+import pytest
+
+from lloyd_data import flop_histograms, synthetic_metric
+from test_oracle_sinkhorn import flop_metric, hist
+
+pytestmark = pytest.mark.gpu
+
+
+def f32eq(a, b):
+    return np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+
+
+def test_reference_property_tests_on_device(rbp):
+    tri = flop_metric()
+    h = hist([(0, 3), (5, 1), (12, 4), (24, 2)])[None]
+    assert abs(rbp.lloyd.sinkhorn_divergence(h, h, [0], [0], tri)[0]) < 1e-4            # sinkhorn.rs divergence_is_zero_on_self
+    mu, nu = hist([(0, 3), (5, 1), (12, 4)])[None], hist([(2, 2), (8, 5), (20, 1), (24, 3)])[None]
+    d12 = rbp.lloyd.sinkhorn_divergence(mu, nu, [0], [0], tri)[0]
+    d21 = rbp.lloyd.sinkhorn_divergence(nu, mu, [0], [0], tri)[0]
+    assert abs(d12 - d21) < 1e-3 and d12 > 0                                            # divergence_is_symmetric
+
+
+@pytest.mark.parametrize("bins,seed", [(32, 0), (256, 1)])
+def test_batched_divergence_bit_exact(rbp, oracle, bins, seed):
+    tri = synthetic_metric(bins, seed)
+    a = flop_histograms(96, bins, seed=seed).astype(np.uint32)
+    b = flop_histograms(64, bins, seed=seed + 10).astype(np.uint32)
+    b[:8] = b[:8] * 1000 + flop_histograms(8, bins, seed=99, draws=400, spread=40.0)    # wide, centroid-like supports
+    rng = np.random.default_rng(seed)
+    ia, ib = rng.integers(0, 96, 400), rng.integers(0, 64, 400)
+    got = rbp.lloyd.sinkhorn_divergence(a, b, ia, ib, tri)
+    want = oracle.sinkhorn_divergence_batch(a[ia], b[ib], tri, math=0)
+    assert f32eq(got, want)
+    # and the contract stays within 2e-5 of the literal libm restatement
+    libm = oracle.sinkhorn_divergence_batch(a[ia[:64]], b[ib[:64]], tri, math=1)
+    assert np.max(np.abs(got[:64] - libm)) < 2e-5
+
+
+@pytest.mark.parametrize("n,k,bins,seed", [(400, 5, 32, 0), (1500, 12, 64, 1), (600, 8, 256, 2)])
+def test_flop_kmeans_bit_exact(rbp, oracle, n, k, bins, seed):
+    pts = flop_histograms(n, bins, seed=seed)
+    tri = synthetic_metric(bins, seed)
+    g = rbp.lloyd.Layer(pts, k, metric=tri)
+    o = oracle.OracleKmeans(pts, k, threads=8)
+    o.set_metric(tri)
+    assert np.array_equal(g.init_centroids(seed), o.init_centroids(seed))
+    g.init_bounds()
+    o.init_bounds()
+    ga, gu, _, _ = g.bounds()
+    oa, ou, _, _ = o.bounds()
+    assert np.array_equal(ga, oa) and f32eq(gu, ou)
+    for it in range(4):
+        s = g.step()
+        drift, sizes, re = o.step()
+        assert f32eq(s.drift, drift), it
+        assert np.array_equal(s.sizes, sizes) and s.reassignment == re, it
+        assert np.array_equal(g.future()[0], o.future()[0]), it
+    ga, gu, gl, gs = g.bounds(True)
+    oa, ou, ol, os_ = o.bounds(True)
+    assert np.array_equal(ga, oa) and f32eq(gu, ou) and f32eq(gl, ol) and np.array_equal(gs, os_)
+    a, d = g.lookup(with_distance=True)
+    oa2, od = o.lookup(with_distance=True)
+    assert np.array_equal(a, oa2) and f32eq(d, od)       # bucket assignments, bit-exact
+    assert f32eq(g.metric(), o.metric())
