@@ -145,6 +145,29 @@ int rbp_river_equity_batch(const uint64_t* pocket, const uint64_t* pub, int64_t 
 int rbp_river_equity_device(const uint64_t* d_pocket, const uint64_t* d_public, int64_t n, float* d_equity, uint8_t* d_bucket,
                             uint32_t* d_wins, uint32_t* d_total, void* stream);
 
+/* ─────────────────────────────── deuce: suit isomorphisms, lookups, projections ─────────────────────────────── */
+
+typedef struct rbp_isoset rbp_isoset_t;
+/* `IsomorphismIterator::from(street)` (crates/deuce/src/isomorphism_iter.rs:7-21): the canonical observations of a
+ * street (0 Pref, 1 Flop, 2 Turn, 3 Rive) in the reference's enumeration order, device-resident, sorted by
+ * (pocket, public).  Sizes: 169 / 1,286,792 / 13,960,050 / 123,156,254 (crates/deuce/src/street.rs:129-135). */
+int rbp_isoset_create(int street, int device, rbp_isoset_t** out);
+void rbp_isoset_destroy(rbp_isoset_t* h);
+int64_t rbp_isoset_size(rbp_isoset_t* h);
+/* copy out a slice: 52-bit card sets (`u64::from(Hand)`), and the abstraction column if attached (nullable pointers) */
+int rbp_isoset_export(rbp_isoset_t* h, int64_t offset, int64_t count, uint64_t* pocket_out, uint64_t* public_out, uint8_t* abs_out);
+/* attach the `Lookup` column isomorphism → abstraction index (e.g. `rbp_kmeans_assign` output narrowed to u8) */
+int rbp_isoset_set_abstractions(rbp_isoset_t* h, const uint8_t* abs);
+/* `Lookup::grow(Street::Rive)` (crates/lloyd/src/lookup.rs:177-184): column = `Abstraction::from(equity)` of every river iso */
+int rbp_isoset_river_buckets(rbp_isoset_t* h);
+/* `Lookup::projections` (lookup.rs:46-66): for parent observations [offset, offset+count) the histogram over the child
+ * street's abstractions of their children (`Observation::children` → `Isomorphism::from` → lookup → `Histogram::increment`):
+ * hist_out[count][bins] u8.  *misses_out counts children not found in the child set (0 when the set is complete). */
+int rbp_isoset_project(rbp_isoset_t* parent, rbp_isoset_t* child, int bins, int64_t offset, int64_t count, uint8_t* hist_out, uint64_t* misses_out);
+/* `Isomorphism::from(Observation)` (crates/deuce/src/isomorphism.rs:9-15, permutation.rs:9-66) for a batch;
+ * flag_out (nullable) = `Isomorphism::is_canonical` */
+int rbp_canonical_batch(const uint64_t* pocket, const uint64_t* pub, int64_t n, uint64_t* pocket_out, uint64_t* public_out, uint8_t* flag_out);
+
 /* ─────────────────────────────── lloyd / elkan: k-means abstraction layers ─────────────────────────────── */
 
 /* distance kinds of `Metric::emd` (crates/lloyd/src/metric.rs:109-115) */

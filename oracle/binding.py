@@ -288,3 +288,56 @@ def sinkhorn_divergence_batch(a, b, tri, math=0, threads=8):
     out = np.zeros(n, np.float32)
     _sink().orc_sinkhorn_divergence_batch(a.ctypes.data, b.ctypes.data, n, bins, tri.ctypes.data, math, out.ctypes.data, threads)
     return out
+
+
+def _iso():
+    l = lib()
+    if not getattr(l, "_iso_ready", False):
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        l.orc_isomorphisms.restype = i64
+        l.orc_isomorphisms.argtypes = [i32, vp, vp, i64, i32]
+        l.orc_canonical_batch.argtypes = [vp, vp, i64, vp, vp, vp]
+        l.orc_turn_histograms.argtypes = [vp, vp, i64, vp, i32]
+        l.orc_project.argtypes = [vp, vp, i64, vp, vp, vp, i64, i32, vp, i32]
+        l._iso_ready = True
+    return l
+
+
+STREETS = {"pref": 0, "flop": 1, "turn": 2, "rive": 3}
+
+
+def isomorphisms(street, cap=None, threads=8):
+    """Canonical observations of a street in `IsomorphismIterator` order → (count, pocket u64[], public u64[])."""
+    l = _iso()
+    st = STREETS[street]
+    n = l.orc_isomorphisms(st, None, None, 0, threads)
+    m = n if cap is None else min(cap, n)
+    pocket, public = np.zeros(m, np.uint64), np.zeros(m, np.uint64)
+    if m:
+        l.orc_isomorphisms(st, pocket.ctypes.data, public.ctypes.data, m, threads)
+    return n, pocket, public
+
+
+def canonical_batch(pocket, public):
+    pocket = np.ascontiguousarray(pocket, dtype=np.uint64)
+    public = np.ascontiguousarray(public, dtype=np.uint64)
+    po, pu, ic = np.zeros_like(pocket), np.zeros_like(public), np.zeros(len(pocket), np.uint8)
+    _iso().orc_canonical_batch(pocket.ctypes.data, public.ctypes.data, len(pocket), po.ctypes.data, pu.ctypes.data, ic.ctypes.data)
+    return po, pu, ic
+
+
+def turn_histograms(pocket, public, threads=8):
+    pocket = np.ascontiguousarray(pocket, dtype=np.uint64)
+    public = np.ascontiguousarray(public, dtype=np.uint64)
+    hist = np.zeros((len(pocket), 101), np.uint8)
+    _iso().orc_turn_histograms(pocket.ctypes.data, public.ctypes.data, len(pocket), hist.ctypes.data, threads)
+    return hist
+
+
+def project(pocket, public, next_pocket, next_public, next_abs, bins, threads=8):
+    a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (pocket, public, next_pocket, next_public)]
+    next_abs = np.ascontiguousarray(next_abs, dtype=np.uint8)
+    hist = np.zeros((len(a[0]), bins), np.uint8)
+    _iso().orc_project(a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, next_abs.ctypes.data, len(a[2]), bins,
+                       hist.ctypes.data, threads)
+    return hist

@@ -522,7 +522,10 @@ struct Solver {
             InfoView v = view_of(profile, info);  // regret matching on the pre-fold regrets
             for (int a = 0; a < v.n; ++a) {
                 Encounter& e = profile.mut_row(info, a);
-                if (t.na[a] > 0) { e.regret = regret_gain(regret_sched, e.regret, t.dr[a], epoch, profile.hyper); updates += t.na[a]; }
+                if (t.na[a] > 0) {
+                    e.regret = regret_gain(regret_sched, e.regret, t.dr[a], epoch, profile.hyper);
+                    updates += gathered[(size_t)(world > 1 ? world_rank : 0) * I + x].na[a];  // telemetry counts this rank's own trees
+                }
                 e.weight = weight_learn(weight_sched, e.weight, (float)t.n * (v.r[a] / v.rd), epoch);
                 const float mean = t.pay / (float)t.n;
                 e.payoff += (mean - e.payoff) * (float)t.n / (float)(e.visits + t.n);

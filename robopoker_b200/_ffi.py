@@ -92,6 +92,16 @@ def load_library():
     l.rbp_kmeans_timed.argtypes = [vp, i32, i32, f32p]
     l.rbp_kmeans_set_metric.argtypes = [vp, vp, i32]
     l.rbp_sinkhorn_batch.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp, ctypes.c_float, i32, ctypes.c_float, vp]
+    l.rbp_isoset_create.argtypes = [i32, i32, P(vp)]
+    l.rbp_isoset_destroy.argtypes = [vp]
+    l.rbp_isoset_destroy.restype = None
+    l.rbp_isoset_size.argtypes = [vp]
+    l.rbp_isoset_size.restype = i64
+    l.rbp_isoset_export.argtypes = [vp, i64, i64, vp, vp, vp]
+    l.rbp_isoset_set_abstractions.argtypes = [vp, vp]
+    l.rbp_isoset_river_buckets.argtypes = [vp]
+    l.rbp_isoset_project.argtypes = [vp, vp, i32, i64, i64, vp, P(u64)]
+    l.rbp_canonical_batch.argtypes = [vp, vp, i64, vp, vp, vp]
     _lib = l
     return l
 

@@ -22,6 +22,7 @@ SOURCES = {
     "flat_game.cpp": ["-Xcompiler", "-ffp-contract=off"],
     "mccfr.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
     "deuce.cu": ["-fmad=false"],
+    "iso.cu": ["-fmad=false"],
     "lloyd_w1.cu": ["-fmad=false"],
     "lloyd_sk.cu": ["-fmad=false"],
     "kmeans_api.cu": ["-fmad=false"],

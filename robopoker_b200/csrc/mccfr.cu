@@ -634,7 +634,7 @@ __device__ __forceinline__ float regret_gain_rt(const EpochArgs& ep, float net, 
 }
 // world level + schedules: sum the ranks' partials in rank order, then ONE schedule application per row
 __global__ void __launch_bounds__(128)
-mccfr_apply_batched_kernel(DevGame g, rbp_encounter_t* __restrict__ table, const Partial* __restrict__ gathered, int world,
+mccfr_apply_batched_kernel(DevGame g, rbp_encounter_t* __restrict__ table, const Partial* __restrict__ gathered, int world, int rank,
                            EpochArgs ep, unsigned long long* __restrict__ counters) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, I = g.n_infos;
     if (x >= I) return;
@@ -653,7 +653,7 @@ mccfr_apply_batched_kernel(DevGame g, rbp_encounter_t* __restrict__ table, const
     unsigned long long ups = 0;
     for (int a = 0; a < A; ++a) {
         rbp_encounter_t e = table[row + a];
-        if (na[a] > 0) { e.regret = regret_gain_rt(ep, e.regret, dr[a]); ups += na[a]; }
+        if (na[a] > 0) { e.regret = regret_gain_rt(ep, e.regret, dr[a]); ups += gathered[(size_t)rank * I + x].na[a]; }  // telemetry counts this rank's own trees
         const float add = (float)n * (r[a] / rd);
         float acc;
         switch (ep.weight_sched) {
@@ -851,7 +851,7 @@ int launch_rank_partial(rbp_solver* s) {
     return RBP_OK;
 }
 int launch_apply_batched(rbp_solver* s, const EpochArgs& ep, const Partial* gathered, int world) {
-    mccfr_apply_batched_kernel<<<(s->dev.n_infos + 127) / 128, 128, 0, s->stream>>>(s->dev, s->table, gathered, world, ep, s->sc.counters);
+    mccfr_apply_batched_kernel<<<(s->dev.n_infos + 127) / 128, 128, 0, s->stream>>>(s->dev, s->table, gathered, world, world > 1 ? s->world_rank : 0, ep, s->sc.counters);
     RBP_LAUNCHED();
     return RBP_OK;
 }

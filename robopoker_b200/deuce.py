@@ -46,3 +46,66 @@ def river_equity(pocket, public):
     _ffi.check(l.rbp_river_equity_batch(pocket.ctypes.data, public.ctypes.data, n, eq.ctypes.data, bk.ctypes.data, w.ctypes.data, t.ctypes.data),
                "rbp_river_equity_batch")
     return eq, bk, w, t
+
+
+STREETS = {"pref": 0, "flop": 1, "turn": 2, "rive": 3}
+
+
+def canonical(pocket, public):
+    """Batch `Isomorphism::from(Observation)`; returns (pocket, public, was_canonical)."""
+    l = _ffi.lib()
+    pocket = np.ascontiguousarray(pocket, dtype=np.uint64)
+    public = np.ascontiguousarray(public, dtype=np.uint64)
+    po, pu, fl = np.zeros_like(pocket), np.zeros_like(public), np.zeros(len(pocket), np.uint8)
+    _ffi.check(l.rbp_canonical_batch(pocket.ctypes.data, public.ctypes.data, len(pocket), po.ctypes.data, pu.ctypes.data, fl.ctypes.data),
+               "rbp_canonical_batch")
+    return po, pu, fl
+
+
+class IsoSet:
+    """`IsomorphismIterator::from(street)` materialised on the device, plus its `Lookup` column (iso → abstraction)."""
+
+    def __init__(self, street, device=0):
+        self._lib = _ffi.lib()
+        self._h = ctypes.c_void_p()
+        self.street = street
+        _ffi.check(self._lib.rbp_isoset_create(STREETS[street], device, ctypes.byref(self._h)), "rbp_isoset_create")
+
+    def __len__(self):
+        return int(self._lib.rbp_isoset_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.rbp_isoset_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def export(self, offset=0, count=None, with_abs=False):
+        count = len(self) - offset if count is None else count
+        p, b = np.zeros(count, np.uint64), np.zeros(count, np.uint64)
+        a = np.zeros(count, np.uint8) if with_abs else None
+        _ffi.check(self._lib.rbp_isoset_export(self._h, offset, count, p.ctypes.data, b.ctypes.data, a.ctypes.data if with_abs else None),
+                   "rbp_isoset_export")
+        return (p, b, a) if with_abs else (p, b)
+
+    def set_abstractions(self, abs_):
+        abs_ = np.ascontiguousarray(abs_, dtype=np.uint8)
+        assert len(abs_) == len(self)
+        _ffi.check(self._lib.rbp_isoset_set_abstractions(self._h, abs_.ctypes.data), "rbp_isoset_set_abstractions")
+
+    def river_buckets(self):
+        """`Lookup::grow(Street::Rive)`."""
+        _ffi.check(self._lib.rbp_isoset_river_buckets(self._h), "rbp_isoset_river_buckets")
+
+    def project(self, child, bins, offset=0, count=None):
+        """`Lookup::projections`: histograms u8[count][bins] of this street's observations over `child`'s abstractions."""
+        count = len(self) - offset if count is None else count
+        hist = np.zeros((count, bins), np.uint8)
+        miss = ctypes.c_uint64()
+        _ffi.check(self._lib.rbp_isoset_project(self._h, child._h, bins, offset, count, hist.ctypes.data, ctypes.byref(miss)), "rbp_isoset_project")
+        return hist, miss.value
