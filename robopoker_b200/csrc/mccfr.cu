@@ -564,8 +564,22 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
                     if (!MASKED || (s_mask[e] >> lane & 1u)) { R = regret_gain<RS>(rc, R, d[e]); ++ups; }
                 }
             } else if (uniform_visits) {  // solver.rs:174-192 update_payoff (Welford) then update_visits
-#pragma unroll 8
-                for (int e = 0; e < chunk_total; ++e) ev += div_by_count(s_pay[e] - ev, s_cnt[e], s_rcp[e]);
+                // operands are pulled into registers 8 entries at a time (LDS.128), so only the arithmetic is on the chain
+                int e = 0;
+                for (; e + 8 <= chunk_total; e += 8) {
+                    const float4 p0 = *reinterpret_cast<const float4*>(s_pay + e), p1 = *reinterpret_cast<const float4*>(s_pay + e + 4);
+                    const float4 c0 = *reinterpret_cast<const float4*>(s_cnt + e), c1 = *reinterpret_cast<const float4*>(s_cnt + e + 4);
+                    const float4 r0 = *reinterpret_cast<const float4*>(s_rcp + e), r1 = *reinterpret_cast<const float4*>(s_rcp + e + 4);
+                    ev += div_by_count(p0.x - ev, c0.x, r0.x);
+                    ev += div_by_count(p0.y - ev, c0.y, r0.y);
+                    ev += div_by_count(p0.z - ev, c0.z, r0.z);
+                    ev += div_by_count(p0.w - ev, c0.w, r0.w);
+                    ev += div_by_count(p1.x - ev, c1.x, r1.x);
+                    ev += div_by_count(p1.y - ev, c1.y, r1.y);
+                    ev += div_by_count(p1.z - ev, c1.z, r1.z);
+                    ev += div_by_count(p1.w - ev, c1.w, r1.w);
+                }
+                for (; e < chunk_total; ++e) ev += div_by_count(s_pay[e] - ev, s_cnt[e], s_rcp[e]);
                 visits += (uint32_t)chunk_total;
             } else {
                 for (int e = 0; e < chunk_total; ++e) {
