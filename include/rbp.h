@@ -216,6 +216,9 @@ int rbp_kmeans_centroids(rbp_kmeans_t* h, uint64_t* counts_out, uint64_t* weight
 int rbp_kmeans_metric(rbp_kmeans_t* h, float* tri_out);
 /* `Bounds<K>` state per point (elkan/src/bounds.rs:19-28) for inspection: assign[n], upper[n], lower[n][k], stale[n] */
 int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, float* lower_out, uint8_t* stale_out);
+/* measurement utility: sustained independent FP32 adds per second (in 1e12/s) on this GPU — the issue ceiling the
+ * W1 distance kernels (202 FADD per distance, no FMA possible) are reported against */
+int rbp_measure_fadd_peak(float* tera_adds_per_s);
 /* CUDA-event timing on the library stream: what = 0 full step, 1 N x K assignment sweep */
 int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out);
 

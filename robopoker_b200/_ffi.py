@@ -90,6 +90,7 @@ def load_library():
     l.rbp_kmeans_metric.argtypes = [vp, vp]
     l.rbp_kmeans_bounds.argtypes = [vp, vp, vp, vp, vp]
     l.rbp_kmeans_timed.argtypes = [vp, i32, i32, f32p]
+    l.rbp_measure_fadd_peak.argtypes = [f32p]
     l.rbp_kmeans_set_metric.argtypes = [vp, vp, i32]
     l.rbp_sinkhorn_batch.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp, ctypes.c_float, i32, ctypes.c_float, vp]
     l.rbp_isoset_create.argtypes = [i32, i32, P(vp)]

@@ -43,7 +43,42 @@ using namespace rbp;
 #define SK(h) reinterpret_cast<KmSk*>(h)
 #define DISPATCH(h, call_w1, call_sk) (!(h) ? RBP_ERR_INVALID : ((h)->kind == RBP_KMEANS_W1 ? (call_w1) : (call_sk)))
 
+namespace rbp {
+// dependent-free FADD streams: the FP32-add issue ceiling the W1 distance kernels are measured against
+__global__ void __launch_bounds__(256) fadd_peak_kernel(float* out, int iters, float seed) {
+    float a0 = seed + threadIdx.x, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float d = seed * 1.0e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 += d; a1 += d; a2 += d; a3 += d; a4 += d; a5 += d; a6 += d; a7 += d;
+        a0 += a4; a1 += a5; a2 += a6; a3 += a7; a4 += d; a5 += d; a6 += d; a7 += d;
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+}  // namespace rbp
+
 extern "C" {
+
+int rbp_measure_fadd_peak(float* tera_adds_per_s) {
+    if (!tera_adds_per_s) return RBP_ERR_INVALID;
+    if (rbp_device_count() < 1) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
+    float* d = nullptr;
+    RBP_CUDA(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    RBP_CUDA(cudaEventCreate(&e0));
+    RBP_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000, blocks = 148 * 8;
+    fadd_peak_kernel<<<blocks, 256>>>(d, 1000, 1.0f);
+    RBP_CUDA(cudaEventRecord(e0));
+    fadd_peak_kernel<<<blocks, 256>>>(d, iters, 1.0f);
+    RBP_LAUNCHED();
+    RBP_CUDA(cudaEventRecord(e1));
+    RBP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    RBP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *tera_adds_per_s = (float)((double)blocks * 256 * 16.0 * iters / (ms * 1e-3) / 1e12);
+    cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return RBP_OK;
+}
 
 int rbp_kmeans_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int device, rbp_kmeans_t** out) {
     if (!out) return RBP_ERR_INVALID;

@@ -33,6 +33,9 @@ def main():
     except Exception:
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
+    import ctypes
+    fadd = ctypes.c_float()
+    rbp.load_library().rbp_measure_fadd_peak(ctypes.byref(fadd))
     pts = turn_histograms(args.n, seed=0)
     for k in args.k:
         g = rbp.lloyd.Layer(pts, k)
@@ -46,7 +49,8 @@ def main():
         line = {"bench": "lloyd_turn_w1", "n": args.n, "k": k, "iters": args.iters,
                 "s_per_iteration": ms_step * 1e-3, "init_pp_s": t_pp, "init_bounds_s": t_bounds,
                 "assign_sweep_ms": ms_assign, "assign_distance_evals_per_s": args.n * k / (ms_assign * 1e-3),
-                "assign_fp32_tflops": args.n * k * 202 / (ms_assign * 1e-3) / 1e12,
+                "assign_fp32_tera_adds": args.n * k * 202 / (ms_assign * 1e-3) / 1e12, "measured_fadd_peak_tera_adds": fadd.value,
+                "assign_frac_of_fadd_peak": args.n * k * 202 / (ms_assign * 1e-3) / 1e12 / fadd.value,
                 "roofline": {"bound": "hbm", "kernel": "elkan_step_kernel", "achieved": bytes_step / (ms_step * 1e-3) / 1e9, "peak": hbm,
                              "unit": "GB/s", "frac": bytes_step / (ms_step * 1e-3) / 1e9 / hbm,
                              "note": "whole step (pairwise+step+accumulate+cdf+drift kernels) over the step kernel's algorithmic bytes"}}
