@@ -173,8 +173,15 @@ class OracleKmeans:
             l.orc_kmeans_init_pp.argtypes = [vp, ctypes.c_uint64, vp]
             l.orc_kmeans_set_centroids_from_points.argtypes = [vp, vp]
             l.orc_kmeans_init_bounds.argtypes = [vp]
+            l.orc_kmeans_set_centroids.argtypes = [vp, vp]
             l.orc_kmeans_step.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_uint32)]
             l.orc_kmeans_state.argtypes = [vp, vp, vp, vp, vp]
+            l.orc_kmeans_step_local.argtypes = [vp]
+            l.orc_kmeans_step_finish.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_uint32)]
+            l.orc_kmeans_acc.restype = ctypes.POINTER(ctypes.c_uint64)
+            l.orc_kmeans_acc.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+            l.orc_kmeans_tally.restype = ctypes.POINTER(ctypes.c_uint32)
+            l.orc_kmeans_tally.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
             l.orc_kmeans_centroids.argtypes = [vp, vp, vp]
             l.orc_kmeans_assign.argtypes = [vp, vp, vp]
             l.orc_kmeans_metric.argtypes = [vp, vp]
@@ -205,12 +212,34 @@ class OracleKmeans:
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         self._l.orc_kmeans_set_centroids_from_points(self._h, idx.ctypes.data)
 
+    def set_centroids_from_counts(self, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        assert counts.shape == (self.k, self.bins)
+        self._l.orc_kmeans_set_centroids(self._h, counts.ctypes.data)
+
     def init_bounds(self):
         self._l.orc_kmeans_init_bounds(self._h)
 
     def step(self):
         drift, sizes, re = np.zeros(self.k, np.float32), np.zeros(self.k, np.uint32), ctypes.c_uint32()
         self._l.orc_kmeans_step(self._h, drift.ctypes.data, sizes.ctypes.data, ctypes.byref(re))
+        return drift, sizes, re.value
+
+    def step_local(self):
+        self._l.orc_kmeans_step_local(self._h)
+
+    def exchange_arrays(self):
+        """numpy views of this shard's integer accumulators (u64) and tallies (u32): all-reduce(sum) them in place."""
+        n = ctypes.c_int64()
+        pa = self._l.orc_kmeans_acc(self._h, ctypes.byref(n))
+        acc = np.ctypeslib.as_array(pa, shape=(n.value,))
+        pt = self._l.orc_kmeans_tally(self._h, ctypes.byref(n))
+        tally = np.ctypeslib.as_array(pt, shape=(n.value,))
+        return acc, tally
+
+    def step_finish(self):
+        drift, sizes, re = np.zeros(self.k, np.float32), np.zeros(self.k, np.uint32), ctypes.c_uint32()
+        self._l.orc_kmeans_step_finish(self._h, drift.ctypes.data, sizes.ctypes.data, ctypes.byref(re))
         return drift, sizes, re.value
 
     def bounds(self, with_lower=False):

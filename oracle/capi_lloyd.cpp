@@ -36,9 +36,26 @@ void orc_kmeans_set_centroids_from_points(Kmeans* m, const int* idx) {
     for (int j = 0; j < m->K; ++j) m->set_centroid_from_point(j, idx[j]);
     if (m->kind == 1) Kmeans::centroid_measures(*m, m->ccounts, m->cmeas, m->cself);
 }
+void orc_kmeans_set_centroids(Kmeans* m, const uint64_t* counts) {
+    for (int j = 0; j < m->K; ++j) {
+        uint64_t w = 0;
+        for (int b = 0; b < m->B; ++b) { m->ccounts[(size_t)j * m->B + b] = counts[(size_t)j * m->B + b]; w += counts[(size_t)j * m->B + b]; }
+        m->cweight[j] = w;
+    }
+    if (m->kind == 1) Kmeans::centroid_measures(*m, m->ccounts, m->cmeas, m->cself);
+}
 void orc_kmeans_init_bounds(Kmeans* m) { m->init_bounds(); }
 void orc_kmeans_step(Kmeans* m, float* drift, uint32_t* sizes, uint32_t* reassigned) {
     Kmeans::StepOut o = m->step();
+    if (drift) std::memcpy(drift, o.drift.data(), o.drift.size() * sizeof(float));
+    if (sizes) std::memcpy(sizes, o.sizes.data(), o.sizes.size() * sizeof(uint32_t));
+    if (reassigned) *reassigned = o.reassigned;
+}
+void orc_kmeans_step_local(Kmeans* m) { m->step_local(); }
+uint64_t* orc_kmeans_acc(Kmeans* m, int64_t* n) { *n = (int64_t)m->acc.size(); return m->acc.data(); }
+uint32_t* orc_kmeans_tally(Kmeans* m, int64_t* n) { *n = (int64_t)m->tally.size(); return m->tally.data(); }
+void orc_kmeans_step_finish(Kmeans* m, float* drift, uint32_t* sizes, uint32_t* reassigned) {
+    Kmeans::StepOut o = m->step_finish();
     if (drift) std::memcpy(drift, o.drift.data(), o.drift.size() * sizeof(float));
     if (sizes) std::memcpy(sizes, o.sizes.data(), o.sizes.size() * sizeof(uint32_t));
     if (reassigned) *reassigned = o.reassigned;

@@ -179,8 +179,16 @@ struct Kmeans {
     }
 
     struct StepOut { std::vector<float> drift; std::vector<uint32_t> sizes; uint32_t reassigned; };
-    // elkan.rs:153-168 step_elkan
+    // elkan.rs:153-168 step_elkan, split at the one exchange point of a point-sharded run: `step_local` is the point
+    // pass plus this shard's integer accumulators [K][B+1] (counts, weight) and tallies; `step_finish` consumes the
+    // (all-reduced) accumulators.  step() = both.
+    std::vector<uint64_t> acc;        // [K][B + 1]
+    std::vector<uint32_t> tally;      // sizes[K] + reassigned
     StepOut step() {
+        step_local();
+        return step_finish();
+    }
+    void step_local() {
         prior = assign;
         std::vector<float> pair((size_t)K * K, 0.0f), mid(K, FLT_MAX);
         parallel(K, [&](int i) {  // elkan.rs:80-93 pairwises (both triangles computed)
@@ -210,11 +218,21 @@ struct Kmeans {
             }
         });
         // elkan.rs:125-142 recompute: integer merge of member points (bins.rs:75-82)
-        std::vector<uint64_t> nc((size_t)K * B, 0), nw(K, 0);
+        acc.assign((size_t)K * (B + 1), 0);
+        tally.assign(K + 1, 0);
         for (int i = 0; i < N; ++i) {
             uint32_t j = assign[i];
-            nw[j] += pweight[i];
-            for (int b = 0; b < B; ++b) nc[(size_t)j * B + b] += points[(size_t)i * B + b];
+            acc[(size_t)j * (B + 1) + B] += pweight[i];
+            for (int b = 0; b < B; ++b) acc[(size_t)j * (B + 1) + b] += points[(size_t)i * B + b];
+            tally[j]++;                      // elkan/src/prior.rs:35-47
+            tally[K] += assign[i] != prior[i];
+        }
+    }
+    StepOut step_finish() {
+        std::vector<uint64_t> nc((size_t)K * B, 0), nw(K, 0);
+        for (int j = 0; j < K; ++j) {
+            nw[j] = acc[(size_t)j * (B + 1) + B];
+            for (int b = 0; b < B; ++b) nc[(size_t)j * B + b] = acc[(size_t)j * (B + 1) + b];
         }
         StepOut out;
         out.drift.resize(K);
@@ -232,9 +250,8 @@ struct Kmeans {
         });
         ccounts.swap(nc); cweight.swap(nw);
         if (kind == 1) { cmeas.swap(nmeas); cself.swap(nself); }
-        out.sizes.assign(K, 0);
-        out.reassigned = 0;
-        for (int i = 0; i < N; ++i) { out.sizes[assign[i]]++; out.reassigned += assign[i] != prior[i]; }  // elkan/src/prior.rs:35-47
+        out.sizes.assign(tally.begin(), tally.begin() + K);
+        out.reassigned = tally[K];
         return out;
     }
 

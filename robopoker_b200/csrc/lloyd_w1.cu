@@ -221,6 +221,9 @@ assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ o
 __global__ void __launch_bounds__(kThreads)
 elkan_step_kernel(KmDev km) {
     extern __shared__ __align__(16) float s_cdf[];
+    float* s_drift = s_cdf + (size_t)min(km.k, kTileK) * kCdfRow;  // [K] drift of the previous step
+    for (int j = threadIdx.x; j < km.k; j += blockDim.x) s_drift[j] = km.pending ? km.drift[j] : 0.0f;
+    __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
     const bool live = i < km.n;
     float X[kBins];
@@ -236,7 +239,7 @@ elkan_step_kernel(KmDev km) {
         c = c_prior = km.assign[i];
         u = km.upper[i];
         stale = km.stale[i] != 0;
-        if (km.pending) { u += km.drift[c]; stale = true; }  // Bounds::update of the previous step (bounds.rs:65-74)
+        if (km.pending) { u += s_drift[c]; stale = true; }  // Bounds::update of the previous step (bounds.rs:65-74)
     }
     const bool act = live && u > km.mid[c];  // step_elkan filter: b.u() > midpoints[b.j()]
     // refresh (elkan.rs:113-117, bounds.rs:76-80): recompute the stale upper bound exactly; lower[c] is written below
@@ -258,22 +261,36 @@ elkan_step_kernel(KmDev km) {
         __syncthreads();
         stage_cdf_tile(s_cdf, km.cdf, j0, kt);
         __syncthreads();
+        // software pipeline: the bounds and the pairwise row of group g+1 are requested before group g is worked on,
+        // so their HBM/L2 latency hides behind the 808 FADDs of the current group
+        float ln[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float4 prn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        uint32_t c_pref = c;
+        auto prefetch = [&](int jj) {
+            const int g_n = min(4, kt - jj);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ln[g] = (g < g_n && live) ? km.lower[(size_t)(j0 + jj + g) * km.n + i] : 0.0f;
+            prn = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
+            c_pref = c;
+        };
+        prefetch(0);
         for (int jj = 0; jj < kt; jj += 4) {
             const int g_n = min(4, kt - jj);
             float l[4], half[4];
             bool want = false;
             uint32_t c_row = c;
-            {   // 0.5 * pairwise[c][j..j+3]: one 16-byte gather per group (rows are padded to a multiple of 4)
-                const float4 pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
-                half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
-            }
+            float4 pr = prn;
+            if (c_pref != c) pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);  // reassigned since the prefetch
+            half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) l[g] = ln[g];
+            if (jj + 4 < kt) prefetch(jj + 4);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                l[g] = 0.0f;
                 if (g < g_n && live) {
                     const int j = j0 + jj + g;
-                    float v = km.lower[(size_t)j * km.n + i];
-                    if (km.pending) { v = v - km.drift[j]; v = v > 0.0f ? v : 0.0f; }  // (lower - movement).max(0.0)
+                    float v = l[g];
+                    if (km.pending) { v = v - s_drift[j]; v = v > 0.0f ? v : 0.0f; }  // (lower - movement).max(0.0)
                     if (refreshed && (uint32_t)j == c_refresh) v = refreshed_d;        // Bounds::refresh sets lower[j]
                     l[g] = v;
                     // could this centroid be examined under the current (c, u)?  (re-tested exactly below)
@@ -294,8 +311,8 @@ elkan_step_kernel(KmDev km) {
                 if (g < g_n && live) {
                     const int j = j0 + jj + g;
                     if (c != c_row) {  // the pairwise row switches when the point is reassigned mid-loop
-                        const float4 pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
-                        half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
+                        const float4 p2 = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
+                        half[0] = 0.5f * p2.x; half[1] = 0.5f * p2.y; half[2] = 0.5f * p2.z; half[3] = 0.5f * p2.w;
                         c_row = c;
                     }
                     if (want && act && (uint32_t)j != c && u > l[g] && u > half[g]) {  // bounds.rs:57-61 has_shifted
@@ -520,7 +537,7 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     h->smem = (size_t)std::min(k, kTileK) * kCdfRow * sizeof(float);
     if (cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaFuncSetAttribute(assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(elkan_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -598,7 +615,7 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.reassigned, 0, sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
-    elkan_step_kernel<<<h->nb, kThreads, h->smem, h->stream>>>(d);
+    elkan_step_kernel<<<h->nb, kThreads, h->smem + (size_t)d.k * sizeof(float), h->stream>>>(d);
     RBP_LAUNCHED();
     {
         const size_t acc_smem = (size_t)d.k * (kBins + 1) * sizeof(unsigned int);

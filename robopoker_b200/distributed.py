@@ -63,6 +63,21 @@ class ShardedSolver:
         return self
 
 
+def sharded_kmeans_step(layer, dist):
+    """`Elkan::step_elkan` over point shards for any layer object exposing `step_local / exchange_arrays / step_finish`
+    with host (numpy) accumulators — the CPU oracle in the gloo tests.  Integer sums: exact in any reduction order."""
+    import torch
+
+    layer.step_local()
+    acc, tally = layer.exchange_arrays()
+    if dist is not None and dist.get_world_size() > 1:
+        ta = torch.from_numpy(acc.view(np.int64))
+        tt = torch.from_numpy(tally.view(np.int32))
+        dist.all_reduce(ta)
+        dist.all_reduce(tt)
+    return layer.step_finish()
+
+
 def allreduce_kmeans_step(layer, dist, device=None):
     """`Elkan::step_elkan` for point-sharded ranks: local point pass, integer all-reduce of the centroid
     accumulators and tallies, then the centroid/drift update — identical on every rank."""

@@ -70,3 +70,51 @@ def test_batched_fold_converges(oracle):
     s.set_fold(1)
     s.step(512)
     assert s.exploitability() < 0.080  # the reference's Leduc threshold (crates/leduc/src/solver.rs:121-123)
+
+
+def _kmeans_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from lloyd_data import turn_histograms
+
+    from oracle import binding as oracle
+    from robopoker_b200.distributed import sharded_kmeans_step
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pts = turn_histograms(3000, seed=5)
+    full = oracle.OracleKmeans(pts, 12, threads=2)
+    chosen = full.init_centroids(4)                      # seeding on the full set (replicated)
+    lo, hi = 3000 * rank // world, 3000 * (rank + 1) // world
+    shard = oracle.OracleKmeans(pts[lo:hi], 12, threads=2)
+    shard.set_centroids_from_counts(pts[chosen].astype(np.uint64))
+    shard.init_bounds()
+    drifts = []
+    for _ in range(5):
+        d, sizes, re = sharded_kmeans_step(shard, dist)
+        drifts.append(d)
+    np.save(os.path.join(out_dir, f"kassign{rank}.npy"), shard.bounds()[0])
+    np.save(os.path.join(out_dir, f"kcent{rank}.npy"), shard.future()[0])
+    np.save(os.path.join(out_dir, f"kdrift{rank}.npy"), np.stack(drifts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_kmeans_allreduce_matches_single_process(tmp_path, oracle):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from lloyd_data import turn_histograms
+
+    world = 2
+    mp.spawn(_kmeans_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    pts = turn_histograms(3000, seed=5)
+    one = oracle.OracleKmeans(pts, 12, threads=4)
+    one.init_centroids(4)
+    one.init_bounds()
+    drifts = np.stack([one.step()[0] for _ in range(5)])
+    assign = np.concatenate([np.load(tmp_path / f"kassign{r}.npy") for r in range(world)])
+    assert np.array_equal(assign, one.bounds()[0])                                   # sharding changes nothing
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"kcent{r}.npy"), one.future()[0])  # centroids identical on every rank
+        assert np.array_equal(np.load(tmp_path / f"kdrift{r}.npy").view(np.uint32), drifts.view(np.uint32))

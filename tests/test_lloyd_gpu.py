@@ -70,3 +70,41 @@ def test_properties_at_scale(rbp):
     a1 = g.lookup()
     a2 = g.lookup()
     assert np.array_equal(a1, a2) and a1.max() < k              # idempotent, in range
+
+
+def test_two_point_shards_on_one_gpu_equal_single_layer(rbp):
+    # point-sharded multi-GPU step emulated in one process: two handles own halves of the points; the integer
+    # accumulators and tallies are summed across the handles (what NCCL all_reduce does), then both finish the step
+    import torch
+
+    from robopoker_b200.distributed import _DeviceWords
+
+    n, k = 6000, 24
+    pts = turn_histograms(n, seed=6)
+    one = rbp.lloyd.Layer(pts, k)
+    chosen = one.init_centroids(2)
+    one.init_bounds()
+    shards = [rbp.lloyd.Layer(pts[: n // 2], k), rbp.lloyd.Layer(pts[n // 2:], k)]
+    for s in shards:
+        s.set_centroids(pts[chosen].astype(np.uint64))
+        s.init_bounds()
+    for it in range(4):
+        ref = one.step()
+        views = []
+        for s in shards:
+            s.step_local()
+            acc_ptr, acc_bytes, sizes_ptr, re_ptr, _ = s.exchange_buffers()
+            views.append((torch.as_tensor(_DeviceWords(acc_ptr, acc_bytes, "<i8", 8), device="cuda"),
+                          torch.as_tensor(_DeviceWords(sizes_ptr, 4 * k, "<i4", 4), device="cuda"),
+                          torch.as_tensor(_DeviceWords(re_ptr, 4, "<i4", 4), device="cuda")))
+        torch.cuda.synchronize()
+        for f in range(3):
+            total = views[0][f] + views[1][f]
+            views[0][f].copy_(total)
+            views[1][f].copy_(total)
+        torch.cuda.synchronize()
+        outs = [s.step_finish() for s in shards]
+        for o in outs:
+            assert f32eq(o.drift, ref.drift) and np.array_equal(o.sizes, ref.sizes) and o.reassignment == ref.reassignment, it
+    assert np.array_equal(np.concatenate([s.bounds()[0] for s in shards]), one.bounds()[0])
+    assert np.array_equal(shards[0].future()[0], one.future()[0])
