@@ -21,6 +21,7 @@
 // drifts are bit-identical to the oracle; the distance itself is only computed when some lane of the warp needs it.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -32,7 +33,9 @@ constexpr int kBins = 101;       // KMEANS_EQTY_CLUSTER_COUNT, crates/pokerkit/s
 constexpr int kRow = 112;        // bytes per stored point row (101 counts + pad, 7 x 16 B)
 constexpr int kCdfRow = 104;     // floats per centroid CDF row in shared memory (26 x LDS.128)
 constexpr int kTileK = 512;      // centroids per shared-memory tile (512 x 104 x 4 B = 208 KB)
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;        // step / k-means++ kernels
+constexpr int kStepThreads = 256;
+constexpr int kAssignThreads = 256;  // assign kernel: 2 blocks x 8 warps per SM at 128 registers
 
 struct KmDev {
     const uint8_t* pts;   // [N][kRow]
@@ -173,10 +176,10 @@ __global__ void metric_normalize_kernel(float* tri, int total) {  // metric.rs:1
 
 // ── naive argmin over all centroids: init_bounds (elkan.rs:39-47), lookup (layer.rs:44-60) ──
 template <bool INIT_BOUNDS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kAssignThreads, 2)
 assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist) {
     extern __shared__ __align__(16) float s_cdf[];
-    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    const int64_t i = blockIdx.x * (int64_t)kAssignThreads + threadIdx.x;
     const bool live = i < km.n;
     float X[kBins];
     if (live) load_point_cdf(km.pts + (size_t)i * kRow, X);
@@ -218,13 +221,14 @@ assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ o
 }
 
 // ── one Elkan step, point side (elkan.rs:153-164 up to recompute) ──
-__global__ void __launch_bounds__(kThreads)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 elkan_step_kernel(KmDev km) {
     extern __shared__ __align__(16) float s_cdf[];
     float* s_drift = s_cdf + (size_t)min(km.k, kTileK) * kCdfRow;  // [K] drift of the previous step
     for (int j = threadIdx.x; j < km.k; j += blockDim.x) s_drift[j] = km.pending ? km.drift[j] : 0.0f;
     __syncthreads();
-    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    const int64_t i = blockIdx.x * (int64_t)THREADS + threadIdx.x;
     const bool live = i < km.n;
     float X[kBins];
     if (live) load_point_cdf(km.pts + (size_t)i * kRow, X);
@@ -537,7 +541,8 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     h->smem = (size_t)std::min(k, kTileK) * kCdfRow * sizeof(float);
     if (cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaFuncSetAttribute(assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(elkan_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -595,7 +600,7 @@ int w1_init_bounds(KmW1* h) {
     if (!h) return RBP_ERR_INVALID;
     if (!h->have_centroids) { set_last_error("init_bounds before centroids"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
-    assign_kernel<true><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
+    assign_kernel<true><<<(unsigned)((h->d.n + kAssignThreads - 1) / kAssignThreads), kAssignThreads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
     RBP_LAUNCHED();
     h->d.pending = 0;
     h->dist_evals += (uint64_t)h->d.n * h->d.k;
@@ -615,7 +620,12 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.reassigned, 0, sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
-    elkan_step_kernel<<<h->nb, kThreads, h->smem + (size_t)d.k * sizeof(float), h->stream>>>(d);
+    {
+        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 0;
+        const size_t sm = h->smem + (size_t)d.k * sizeof(float);
+        if (variant == 1) elkan_step_kernel<256, 2><<<(unsigned)((d.n + 255) / 256), 256, sm, h->stream>>>(d);
+        else elkan_step_kernel<128, 1><<<(unsigned)((d.n + 127) / 128), 128, sm, h->stream>>>(d);
+    }
     RBP_LAUNCHED();
     {
         const size_t acc_smem = (size_t)d.k * (kBins + 1) * sizeof(unsigned int);
@@ -669,7 +679,7 @@ int w1_assign(KmW1* h, uint32_t* assign_out, float* dist_out) {
     if (!h || !assign_out) return RBP_ERR_INVALID;
     if (!h->have_centroids) { set_last_error("assign before centroids"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
-    assign_kernel<false><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+    assign_kernel<false><<<(unsigned)((h->d.n + kAssignThreads - 1) / kAssignThreads), kAssignThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
     RBP_LAUNCHED();
     h->dist_evals += (uint64_t)h->d.n * h->d.k;
     RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -740,7 +750,7 @@ int w1_timed(KmW1* h, int what, int iters, float* ms_out) {
         int st;
         if (what == 0) st = w1_step(h, nullptr, nullptr, nullptr);
         else {
-            assign_kernel<false><<<h->nb, kThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+            assign_kernel<false><<<(unsigned)((h->d.n + kAssignThreads - 1) / kAssignThreads), kAssignThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
             g_launches.fetch_add(1);
             st = cudaGetLastError() == cudaSuccess ? RBP_OK : RBP_ERR_CUDA;
         }

@@ -138,37 +138,7 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
     }
     __syncthreads();
 
-    // Trees of one block are walked in an order sorted by their root deal, so the lanes of a warp hold trees of the
-    // same shape family (same hole cards) and diverge only where sampled opponent actions differ.  Results return to
-    // the tree's own slot before the multisplit, so nothing downstream sees the permutation.
-    __shared__ int s_bin[40];
-    __shared__ uint8_t s_perm[kTreesPerBlock];
-    __shared__ uint8_t s_rn[kTreesPerBlock];                             // records per tree
-    __shared__ uint8_t s_nodes[kTreesPerBlock];                          // nodes per tree (telemetry)
-    __shared__ int16_t s_rinfo[kTreesPerBlock][kMaxRecords];
-    __shared__ uint8_t s_rmask[kTreesPerBlock][kMaxRecords];
-    __shared__ float s_rpay[kTreesPerBlock][kMaxRecords];
-    __shared__ float s_rdr[kTreesPerBlock][kMaxRecords][kMaxActions];
-    if (tid < 40) s_bin[tid] = 0;
-    __syncthreads();
-    int my_bin, my_rank;
-    {
-        const int own = blockIdx.x * kTreesPerBlock + tid;
-        my_bin = 37;  // inactive trees sort last
-        if (own < ep.batch) {
-            Philox4 pr = philox4x32_10(ep.epoch, (uint32_t)(ep.tree_base + own), 0xFFFFFFFFu, TAG_ROOT, ep.seed_lo, ep.seed_hi);
-            const uint32_t i = draw_range(pr.r[0], (uint32_t)g.deck), j = 1u + draw_range(pr.r[1], (uint32_t)g.deck - 1u);
-            my_bin = g.deck <= 6 ? (int)(i * g.deck + ((j == i) ? 0u : j)) : (int)(i % 36u);
-        }
-        my_rank = atomicAdd(&s_bin[my_bin], 1);
-    }
-    __syncthreads();
-    if (tid == 0) { int run = 0; for (int b = 0; b < 40; ++b) { const int c = s_bin[b]; s_bin[b] = run; run += c; } }
-    __syncthreads();
-    s_perm[s_bin[my_bin] + my_rank] = (uint8_t)tid;
-    __syncthreads();
-    const int slot_of_mine = s_perm[tid];   // the tree (slot within the block) this thread walks
-    const int local = blockIdx.x * kTreesPerBlock + slot_of_mine;
+    const int local = blockIdx.x * kTreesPerBlock + tid;
     const bool active = local < ep.batch;
     const uint32_t tree = (uint32_t)(ep.tree_base + local);
 
@@ -324,21 +294,6 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
                 rec_mask[slot] |= (uint8_t)(1u << act[i]);
             }
         }
-    }
-
-    // hand the Decisions back to the tree's own slot, then continue in tree order
-    s_rn[slot_of_mine] = (uint8_t)nrec;
-    s_nodes[slot_of_mine] = (uint8_t)ln;
-    for (int s = 0; s < nrec; ++s) {
-        s_rinfo[slot_of_mine][s] = rec_info[s]; s_rmask[slot_of_mine][s] = rec_mask[s]; s_rpay[slot_of_mine][s] = rec_pay[s];
-        for (int a = 0; a < kMaxActions; ++a) s_rdr[slot_of_mine][s][a] = rec_dr[s][a];
-    }
-    __syncthreads();
-    nrec = s_rn[tid];
-    ln = s_nodes[tid];
-    for (int s = 0; s < nrec; ++s) {
-        rec_info[s] = s_rinfo[tid][s]; rec_mask[s] = s_rmask[tid][s]; rec_pay[s] = s_rpay[tid][s];
-        for (int a = 0; a < kMaxActions; ++a) rec_dr[s][a] = s_rdr[tid][s][a];
     }
 
     // ── stable multisplit of the block's records by infoset (tree order preserved) ──
