@@ -8,14 +8,15 @@
 using namespace orc;
 
 struct OrcSolver {
-    int game;  // 0 kuhn, 1 leduc
+    int game;  // 0 kuhn, 1 leduc, 2 rps
     Solver<KuhnGame> kuhn;
     Solver<LeducGame> leduc;
+    Solver<RpsGame> rps;
 };
 
 template <class F>
 static auto with(OrcSolver* s, F f) {
-    return s->game == 0 ? f(s->kuhn) : f(s->leduc);
+    return s->game == 0 ? f(s->kuhn) : (s->game == 1 ? f(s->leduc) : f(s->rps));
 }
 
 extern "C" {
@@ -33,7 +34,7 @@ void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
 }
 
 OrcSolver* orc_solver_create(int game, int regret, int weight, int sampling, int batch, uint64_t seed, int threads) {
-    if (game < 0 || game > 1) return nullptr;
+    if (game < 0 || game > 2) return nullptr;
     OrcSolver* s = new OrcSolver();
     s->game = game;
     auto init = [&](auto& sv) {

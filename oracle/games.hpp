@@ -232,4 +232,42 @@ struct LeducGame {
     static float default_regret(uint8_t) { return 0.0f; }
 };
 
+// ───────────────────────────── Rock-Paper-Scissors (crates/roshambo/src) ─────────────────────────────
+struct RpsGame {
+    enum Edge : uint8_t { ER = 0, EP = 1, ES = 2 };  // edge.rs:6-10
+    struct State { uint8_t id; };                     // game.rs:6: RpsGame(u8), 0 root, 1-3 after P1, 4-12 terminal
+    static const char* name() { return "rps"; }
+    static State root(const Philox4&) { return State{0}; }            // game.rs:11-13 (no deal)
+    static State exploitability_root() { return State{0}; }
+    static Turn turn(const State& s) { return s.id == 0 ? TURN_P0 : (s.id <= 3 ? TURN_P1 : TURN_TERMINAL); }  // game.rs:14-21
+    static State apply(const State& s, uint8_t e) { return State{(uint8_t)(s.id == 0 ? 1 + e : 4 + 3 * (s.id - 1) + e)}; }  // game.rs:23-39
+    // game.rs:41-63: ASYMMETRIC_UTILITY = 2 (crates/pokerkit/src/lib.rs:198): scissors wins/losses count double
+    static float payoff(const State& s, int p) {
+        const float direction = p == 0 ? 0.0f + 1.0f : 0.0f - 1.0f;
+        float v;
+        switch (s.id) {
+            case 7: v = 0.0f + 1.0f; break;   // P > R
+            case 5: v = 0.0f - 1.0f; break;   // R < P
+            case 6: v = 0.0f + 2.0f; break;   // R > S
+            case 11: v = 0.0f + 2.0f; break;  // S > P
+            case 10: v = 0.0f - 2.0f; break;  // S < R
+            case 9: v = 0.0f - 2.0f; break;   // P < S
+            default: v = 0.0f; break;
+        }
+        return direction * v;
+    }
+    // encoder.rs:15-25: the infoset is the turn itself
+    static uint32_t info_key(const State& s) {
+        Turn t = turn(s);
+        return (t == TURN_TERMINAL ? 0u : 1u) | ((uint32_t)(t == TURN_TERMINAL ? 2 : (int)t) << 1);
+    }
+    static int choices(uint32_t key, uint8_t* out) {  // turn.rs:43-49
+        if (!(key & 1u)) return 0;
+        out[0] = ER; out[1] = EP; out[2] = ES;
+        return 3;
+    }
+    static int branches(const State& s, uint8_t* out) { return turn(s) == TURN_TERMINAL ? 0 : choices(info_key(s), out); }
+    static float default_regret(uint8_t) { return 0.0f; }
+};
+
 }  // namespace orc

@@ -37,8 +37,9 @@ inline int actor_of(uint8_t spot) { return (spot == OPEN || spot == CHECKRAISED)
 inline bool was_raised(uint8_t spot) { return spot == RAISED || spot == CHECKRAISED; }
 
 struct Rules {
-    int rounds;  // 1 = Kuhn, 2 = Leduc
+    int rounds;  // 1 = Kuhn, 2 = Leduc, 0 = Rock-Paper-Scissors (crates/roshambo/src/game.rs: 13 states, id kept in hole[0])
     uint8_t turn(const Pos& p) const {
+        if (rounds == 0) return p.hole[0] == 0 ? TURN_P0 : (p.hole[0] <= 3 ? TURN_P1 : TURN_TERMINAL);  // roshambo game.rs:14-21
         switch (p.phase) {
             case START: case DEALT: case BOARD: return TURN_CHANCE;
             case BET: return (uint8_t)actor_of(p.spot[p.round]);
@@ -48,6 +49,11 @@ struct Rules {
     // children in `branches()` order: deals ascending by card, actions in `choices()` order
     int expand(const Pos& p, Pos* out) const {
         int n = 0;
+        if (rounds == 0) {  // roshambo game.rs:23-39: R, P, S in `choices()` order (turn.rs:43-49)
+            if (p.hole[0] > 3) return 0;
+            for (int e = 0; e < 3; ++e) { Pos q = p; q.hole[0] = (uint8_t)(p.hole[0] == 0 ? 1 + e : 4 + 3 * (p.hole[0] - 1) + e); out[n++] = q; }
+            return n;
+        }
         if (p.phase == START || p.phase == DEALT || p.phase == BOARD) {
             for (int c = 0; c < 6; ++c) {
                 if (p.phase != START && c == p.hole[0]) continue;
@@ -75,6 +81,11 @@ struct Rules {
         return n;
     }
     float payoff(const Pos& p, int me) const {
+        if (rounds == 0) {  // roshambo game.rs:41-63 with ASYMMETRIC_UTILITY = 2 (pokerkit lib.rs:198): scissors counts double
+            static const float first_player[13] = {0, 0, 0, 0, 0, -1, 2, 1, 0, -2, -2, 2, 0};
+            const float v = 0.0f + first_player[p.hole[0]];
+            return (me == 0 ? 1.0f : -1.0f) * v;
+        }
         int r0 = p.hole[0] >> 1, r1 = p.hole[1] >> 1;
         if (rounds == 1) {  // Kuhn
             if (p.phase == FOLDED) return p.who == me ? -1.0f : 1.0f;
@@ -101,6 +112,7 @@ struct Rules {
     }
     // include/rbp.h key layouts
     uint32_t info_key(const Pos& p) const {
+        if (rounds == 0) { const uint8_t t0 = turn(p); return (t0 == TURN_TERMINAL ? 0u : 1u) | ((uint32_t)(t0 == TURN_TERMINAL ? 2 : t0) << 1); }  // encoder.rs:15-25
         uint8_t t = turn(p);
         uint32_t acting = t <= TURN_P1 ? 1u : 0u;
         int actor = t == TURN_P1 ? 1 : 0;
@@ -129,11 +141,11 @@ struct Rules {
 }  // namespace
 
 bool build_flat_game(int game_id, FlatGame* g) {
-    if (game_id != 0 && game_id != 1) return false;
-    Rules rules{game_id == 0 ? 1 : 2};
+    if (game_id < 0 || game_id > 2) return false;
+    Rules rules{game_id == 0 ? 1 : (game_id == 1 ? 2 : 0)};
     *g = FlatGame();
     std::vector<Pos> pos;
-    pos.push_back(Pos{{0, 0}, START, 0, {OPEN, OPEN}, -1, 0});
+    pos.push_back(Pos{{0, 0}, (uint8_t)(game_id == 2 ? BET : START), 0, {OPEN, OPEN}, -1, 0});
     g->parent.push_back(-1);
     std::vector<int> depth{0};
     for (size_t i = 0; i < pos.size(); ++i) {  // breadth-first: children contiguous, levels contiguous
@@ -201,6 +213,10 @@ bool build_flat_game(int game_id, FlatGame* g) {
     }
     g->span_start.push_back((int32_t)g->span_nodes.size());
     // `root()`: hole pair after the two deal edges
+    if (game_id == 2) {  // `RpsGame::root()` is deterministic
+        g->deck = 0;
+        g->root_table.assign(1, 0);
+    } else {
     g->deck = 6;
     g->root_table.assign(36, -1);
     for (int c0 = 0; c0 < 6; ++c0) {
@@ -209,6 +225,7 @@ bool build_flat_game(int game_id, FlatGame* g) {
             if (c1 == c0) continue;
             g->root_table[c0 * 6 + c1] = g->nodes[dealt].first_child + (c1 < c0 ? c1 : c1 - 1);
         }
+    }
     }
     // sizing DP, bottom-up (BFS order ⇒ children have larger ids)
     std::vector<int> mn[2], mi[2], md(N, 0);

@@ -160,11 +160,15 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
 
         // `CfrGame::root()` (kuhn/leduc game.rs root()): two-swap Fisher-Yates of the identity deck
         {
-            Philox4 pr = philox4x32_10(ep.epoch, tree, 0xFFFFFFFFu, TAG_ROOT, ep.seed_lo, ep.seed_hi);
-            uint32_t i = draw_range(pr.r[0], (uint32_t)g.deck);
-            uint32_t j = 1u + draw_range(pr.r[1], (uint32_t)g.deck - 1u);
-            uint32_t c0 = i, c1 = (j == i) ? 0u : j;
-            l_flat[0] = (int16_t)g.root_table[c0 * g.deck + c1];
+            if (g.deck > 1) {
+                Philox4 pr = philox4x32_10(ep.epoch, tree, 0xFFFFFFFFu, TAG_ROOT, ep.seed_lo, ep.seed_hi);
+                uint32_t i = draw_range(pr.r[0], (uint32_t)g.deck);
+                uint32_t j = 1u + draw_range(pr.r[1], (uint32_t)g.deck - 1u);
+                uint32_t c0 = i, c1 = (j == i) ? 0u : j;
+                l_flat[0] = (int16_t)g.root_table[c0 * g.deck + c1];
+            } else {
+                l_flat[0] = (int16_t)g.root_table[0];  // games without a deal (roshambo game.rs:11-13)
+            }
             l_parent[0] = -1; l_act[0] = 0; l_head[0] = -1; l_next[0] = -1;
             ln = 1;
         }

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _ffi
 
-GAMES = {"kuhn": 0, "leduc": 1}
+GAMES = {"kuhn": 0, "leduc": 1, "rps": 2}
 REGRETS = {"SummedRegret": 0, "FlooredRegret": 1, "LinearRegret": 2, "DiscountedRegret": 3, "AsymmetricRegret": 4}
 WEIGHTS = {"ConstantWeight": 0, "LinearWeight": 1, "QuadraticWeight": 2, "ExponentialWeight": 3}
 SAMPLERS = {"ExternalSampling": 0, "VanillaSampling": 1, "PrunableSampling": 2, "PluribusSampling": 3}

@@ -171,3 +171,17 @@ def test_batched_two_ranks_on_one_gpu(rbp, oracle):
             o.fold_gathered(words, 2)
     rows_equal(hs[0].profile_rows(), hs[1].profile_rows())
     rows_equal(hs[0].profile_rows(), os_[0].profile_rows())
+
+
+@pytest.mark.parametrize("fold", [0, 1])
+def test_rps_bit_exact(rbp, oracle, fold):
+    # third validation game (crates/roshambo): 3 actions, no deal, an infoset spanning three nodes of one tree
+    g = rbp.Solver("rps", "DiscountedRegret", "LinearWeight", "PluribusSampling", batch=97, seed=6, fold=fold)
+    o = oracle.OracleSolver("rps", "DiscountedRegret", "LinearWeight", "PluribusSampling", batch=97, seed=6, threads=2)
+    o.set_fold(fold)
+    assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32)
+    g.step(300)
+    o.step(300)
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.counters() == o.counters()
+    assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32)

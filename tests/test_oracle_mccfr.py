@@ -90,3 +90,13 @@ def test_threads_do_not_change_results(oracle):
     a = oracle.OracleSolver("leduc", batch=64, seed=3, threads=1).step(20)
     b = oracle.OracleSolver("leduc", batch=64, seed=3, threads=4).step(20)
     assert a.profile_rows().tobytes() == b.profile_rows().tobytes()
+
+
+def test_rps_equilibrium_and_exploitability(oracle):
+    # crates/roshambo/src/solver.rs:157-165,253-257: asymmetric payoffs (scissors double) -> (0.4, 0.4, 0.2), exploitability < 0.03
+    s = oracle.OracleSolver("rps", "FlooredRegret", "LinearWeight", "ExternalSampling").solve(1 << 16)
+    assert s.tree_stats() == {"nodes": 13, "terminals": 9, "infosets": 2}
+    for key in (1, 3):  # P1, P2
+        r, p, sc = s.averaged_distribution(key)
+        assert abs(r - 0.40) < 0.05 and abs(p - 0.40) < 0.05 and abs(sc - 0.20) < 0.05
+    assert s.exploitability() < 0.03
