@@ -40,7 +40,7 @@ struct Encounter {  // solver/encounter.rs:21-27
 
 enum RegretSched { R_SUMMED = 0, R_FLOORED = 1, R_LINEAR = 2, R_DISCOUNTED = 3, R_ASYMMETRIC = 4 };
 enum WeightSched { W_CONSTANT = 0, W_LINEAR = 1, W_QUADRATIC = 2, W_EXPONENTIAL = 3 };
-enum SamplingKind { S_EXTERNAL = 0, S_VANILLA = 1, S_PRUNABLE = 2, S_PLURIBUS = 3 };
+enum SamplingKind { S_EXTERNAL = 0, S_VANILLA = 1, S_PRUNABLE = 2, S_PLURIBUS = 3, S_TARGETED = 4 };
 enum FoldMode { FOLD_ORDERED = 0, FOLD_BATCHED = 1 };
 
 struct Hyper {
@@ -249,7 +249,7 @@ struct Solver {
         int walker = profile.walker();
         uint32_t epoch = (uint32_t)profile.epochs;
         if ((int)p == walker) {
-            if (kind == S_EXTERNAL) return;  // external.rs:36
+            if (kind == S_EXTERNAL || kind == S_TARGETED) return;  // external.rs:36, targeted.rs:27
             if (kind == S_PLURIBUS) {        // pluribus.rs:85-93
                 if (profile.epochs < profile.hyper.prune_warmup) return;
                 Philox4 c = rng.at(epoch, (uint32_t)tree.id, info, TAG_COIN);
@@ -275,6 +275,11 @@ struct Solver {
             float w[MAX_BRANCH];
             for (size_t i = 0; i < br.size(); ++i) {
                 int a = action_of(v, br[i].edge);
+                if (kind == S_TARGETED) {  // targeted.rs:34-62: iterated distribution floored at `curiosity`
+                    float sg = v.r[a] / v.rd;
+                    w[i] = sg > profile.hyper.curiosity ? sg : profile.hyper.curiosity;
+                    continue;
+                }
                 float q = v.sw[a] / v.z;
                 w[i] = q > EPS ? q : EPS;
             }

@@ -202,14 +202,18 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
             if (nd.turn == TURN_CHANCE) {
                 pick = (int)draw_range(p.r[0], (uint32_t)n);  // sample/mod.rs:68-82
             } else {  // sample/external.rs:42-64
-                const float* q = s_q + nd.info * kMaxActions;
+                // external.rs:42-64: sampling distribution floored at EPSILON; targeted.rs:34-62: iterated distribution
+                // floored at `curiosity`
+                const bool targeted = ep.sampling == RBP_SAMPLING_TARGETED;
+                const float* q = (targeted ? s_sigma : s_q) + nd.info * kMaxActions;
+                const float lo = targeted ? ep.hyper.curiosity : kEps;
                 float total = 0.0f;
-                for (int a = 0; a < n; ++a) total = total + fmax_ref(q[a], kEps);
+                for (int a = 0; a < n; ++a) total = total + fmax_ref(q[a], lo);
                 const float x = draw_unit(p.r[0]) * total;
                 float cum = 0.0f;
                 pick = n - 1;
                 for (int a = 0; a < n; ++a) {
-                    cum = cum + fmax_ref(q[a], kEps);
+                    cum = cum + fmax_ref(q[a], lo);
                     if (x < cum) { pick = a; break; }
                 }
             }
@@ -962,7 +966,7 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
     if (!out) return RBP_ERR_INVALID;
     *out = nullptr;
     if (regret < 0 || regret > 4 || weight < 0 || weight > 3 || batch < 1) return RBP_ERR_INVALID;
-    if (sampling != RBP_SAMPLING_EXTERNAL && sampling != RBP_SAMPLING_PRUNABLE && sampling != RBP_SAMPLING_PLURIBUS) {
+    if (sampling != RBP_SAMPLING_EXTERNAL && sampling != RBP_SAMPLING_PRUNABLE && sampling != RBP_SAMPLING_PLURIBUS && sampling != RBP_SAMPLING_TARGETED) {
         set_last_error("training needs a sampling scheme (VanillaSampling is exploitability-only, sample/vanilla.rs)");
         return RBP_ERR_INVALID;
     }

@@ -12,7 +12,7 @@ from . import _ffi
 GAMES = {"kuhn": 0, "leduc": 1, "rps": 2}
 REGRETS = {"SummedRegret": 0, "FlooredRegret": 1, "LinearRegret": 2, "DiscountedRegret": 3, "AsymmetricRegret": 4}
 WEIGHTS = {"ConstantWeight": 0, "LinearWeight": 1, "QuadraticWeight": 2, "ExponentialWeight": 3}
-SAMPLERS = {"ExternalSampling": 0, "VanillaSampling": 1, "PrunableSampling": 2, "PluribusSampling": 3}
+SAMPLERS = {"ExternalSampling": 0, "VanillaSampling": 1, "PrunableSampling": 2, "PluribusSampling": 3, "TargetedSampling": 4}
 FOLD_ORDERED, FOLD_BATCHED = 0, 1
 
 ROW_DTYPE = np.dtype([("info_key", "<u4"), ("action", "<u4"), ("weight", "<f4"), ("regret", "<f4"), ("payoff", "<f4"),

@@ -41,6 +41,8 @@ CASES = [
     ("leduc", "DiscountedRegret", "LinearWeight", "ExternalSampling", 256, 80),
     ("leduc", "SummedRegret", "ConstantWeight", "PrunableSampling", 500, 40),
     ("leduc", "AsymmetricRegret", "QuadraticWeight", "PluribusSampling", 200, 60),
+    ("leduc", "FlooredRegret", "LinearWeight", "TargetedSampling", 333, 60),
+    ("kuhn", "LinearRegret", "ConstantWeight", "TargetedSampling", 50, 200),
 ]
 
 
