@@ -221,11 +221,11 @@ assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ o
 }
 
 // ── one Elkan step, point side (elkan.rs:153-164 up to recompute) ──
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, int TILE>
 __global__ void __launch_bounds__(THREADS, MINB)
 elkan_step_kernel(KmDev km) {
     extern __shared__ __align__(16) float s_cdf[];
-    float* s_drift = s_cdf + (size_t)min(km.k, kTileK) * kCdfRow;  // [K] drift of the previous step
+    float* s_drift = s_cdf + (size_t)min(km.k, TILE) * kCdfRow;  // [K] drift of the previous step
     for (int j = threadIdx.x; j < km.k; j += blockDim.x) s_drift[j] = km.pending ? km.drift[j] : 0.0f;
     __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)THREADS + threadIdx.x;
@@ -260,8 +260,8 @@ elkan_step_kernel(KmDev km) {
         }
     }
     const uint32_t c_refresh = c;
-    for (int j0 = 0; j0 < km.k; j0 += kTileK) {
-        const int kt = min(kTileK, km.k - j0);
+    for (int j0 = 0; j0 < km.k; j0 += TILE) {
+        const int kt = min(TILE, km.k - j0);
         __syncthreads();
         stage_cdf_tile(s_cdf, km.cdf, j0, kt);
         __syncthreads();
@@ -541,8 +541,9 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     h->smem = (size_t)std::min(k, kTileK) * kCdfRow * sizeof(float);
     if (cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaFuncSetAttribute(assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(elkan_step_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
-        cudaFuncSetAttribute(elkan_step_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 1, kTileK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<256, 2, kTileK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -622,9 +623,10 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
     {
         static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 0;
-        const size_t sm = h->smem + (size_t)d.k * sizeof(float);
-        if (variant == 1) elkan_step_kernel<256, 2><<<(unsigned)((d.n + 255) / 256), 256, sm, h->stream>>>(d);
-        else elkan_step_kernel<128, 1><<<(unsigned)((d.n + 127) / 128), 128, sm, h->stream>>>(d);
+        const size_t drift_b = (size_t)d.k * sizeof(float);
+        if (variant == 1) elkan_step_kernel<256, 2, kTileK><<<(unsigned)((d.n + 255) / 256), 256, h->smem + drift_b, h->stream>>>(d);
+        else if (variant == 2) elkan_step_kernel<128, 3, 128><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
+        else elkan_step_kernel<128, 1, kTileK><<<(unsigned)((d.n + 127) / 128), 128, h->smem + drift_b, h->stream>>>(d);
     }
     RBP_LAUNCHED();
     {
