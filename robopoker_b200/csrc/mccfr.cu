@@ -408,7 +408,7 @@ __device__ __forceinline__ float regret_gain(const RegretConst& c, float net, fl
 // guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
 __device__ __forceinline__ float div_by_count(float a, float b, float rb) {
     // exponent of a within [2^-64, 2^63] (zero takes the slow path too), evaluated beside the FMA chain
-    const bool safe = ((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u && (__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu;
+    const bool safe = ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (a == 0.0f)) & ((__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu);
     const float q = a * rb;
     const float r = __fmaf_rn(-b, q, a);
     const float fast = __fmaf_rn(r, rb, q);
@@ -578,14 +578,26 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
                     const float4 p0 = *reinterpret_cast<const float4*>(s_pay + e), p1 = *reinterpret_cast<const float4*>(s_pay + e + 4);
                     const float4 c0 = *reinterpret_cast<const float4*>(s_cnt + e), c1 = *reinterpret_cast<const float4*>(s_cnt + e + 4);
                     const float4 r0 = *reinterpret_cast<const float4*>(s_rcp + e), r1 = *reinterpret_cast<const float4*>(s_rcp + e + 4);
-                    ev += div_by_count(p0.x - ev, c0.x, r0.x);
-                    ev += div_by_count(p0.y - ev, c0.y, r0.y);
-                    ev += div_by_count(p0.z - ev, c0.z, r0.z);
-                    ev += div_by_count(p0.w - ev, c0.w, r0.w);
-                    ev += div_by_count(p1.x - ev, c1.x, r1.x);
-                    ev += div_by_count(p1.y - ev, c1.y, r1.y);
-                    ev += div_by_count(p1.z - ev, c1.z, r1.z);
-                    ev += div_by_count(p1.w - ev, c1.w, r1.w);
+                    // branch-free fast path for the 8 entries; the guard of div_by_count is accumulated beside the chain
+                    // and, if any entry fell outside it, the group is redone with IEEE division from the saved state
+                    const float ev_in = ev;
+                    bool ok = true;
+                    const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                    const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float a = pv[k] - ev;
+                        ok &= ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (a == 0.0f)) & ((__float_as_uint(cv[k]) & 0x7FFFFFu) != 0x7FFFFFu);
+                        const float q = a * rv[k];
+                        const float r = __fmaf_rn(-cv[k], q, a);
+                        ev += __fmaf_rn(r, rv[k], q);
+                    }
+                    if (__builtin_expect(!ok, 0)) {
+                        ev = ev_in;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ev += (pv[k] - ev) / cv[k];
+                    }
                 }
                 for (; e < chunk_total; ++e) ev += div_by_count(s_pay[e] - ev, s_cnt[e], s_rcp[e]);
                 visits += (uint32_t)chunk_total;
