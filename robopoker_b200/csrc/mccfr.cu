@@ -408,7 +408,7 @@ __device__ __forceinline__ float regret_gain(const RegretConst& c, float net, fl
 // guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
 __device__ __forceinline__ float div_by_count(float a, float b, float rb) {
     // exponent of a within [2^-64, 2^63] (zero takes the slow path too), evaluated beside the FMA chain
-    const bool safe = ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (a == 0.0f)) & ((__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu);
+    const bool safe = ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (__float_as_uint(a) == 0u)) & ((__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu);
     const float q = a * rb;
     const float r = __fmaf_rn(-b, q, a);
     const float fast = __fmaf_rn(r, rb, q);
@@ -588,7 +588,7 @@ mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, Ep
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float a = pv[k] - ev;
-                        ok &= ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (a == 0.0f)) & ((__float_as_uint(cv[k]) & 0x7FFFFFu) != 0x7FFFFFu);
+                        ok &= ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (__float_as_uint(a) == 0u)) & ((__float_as_uint(cv[k]) & 0x7FFFFFu) != 0x7FFFFFu);
                         const float q = a * rv[k];
                         const float r = __fmaf_rn(-cv[k], q, a);
                         ev += __fmaf_rn(r, rv[k], q);
