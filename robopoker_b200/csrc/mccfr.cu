@@ -718,6 +718,8 @@ __global__ void div_selftest_kernel(uint32_t max_count, uint32_t samples, unsign
                 uint32_t expo = 64u + ((bits >> 23) & 0xFFu) % 128u;  // 2^-63 .. 2^64
                 float a = __uint_as_float((bits & 0x807FFFFFu) | (expo << 23));
                 if ((k + j) % 16 == 0) a = (float)((int)(bits % 2001u) - 1000) * 0.25f;  // small payoffs like Leduc's
+                if ((k + j) % 64 == 1) a = 0.0f;
+                if ((k + j) % 64 == 2) a = -0.0f;
                 if (__float_as_uint(div_by_count(a, fb, rb)) != __float_as_uint(a / fb)) ++bad;
             }
         }
