@@ -233,8 +233,15 @@ def main():
         note = ("sampling kernel: latency/divergence-bound tree walks over L1/L2-resident tables (SURVEY 8d: reported, not claimed "
                 "against the HBM roofline); algorithmic bytes = 32 B per infoset-action update")
     achieved = 32.0 * per_launch_updates / dom_s / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]
+        if args.batch == 262144 or dom == "mccfr_fold_kernel":
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
                 "kernel_ms": {"mccfr_sample_kernel": ms_sample / args.steps, "fold_kernels": ms_fold / args.steps}, "note": note}
 
     if rank == 0:
