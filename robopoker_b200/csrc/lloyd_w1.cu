@@ -622,7 +622,7 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
     {
-        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 0;
+        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 2;  // 2 = 3 blocks/SM, 128-centroid tiles (fastest measured)
         const size_t drift_b = (size_t)d.k * sizeof(float);
         if (variant == 1) elkan_step_kernel<256, 2, kTileK><<<(unsigned)((d.n + 255) / 256), 256, h->smem + drift_b, h->stream>>>(d);
         else if (variant == 2) elkan_step_kernel<128, 3, 128><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
