@@ -370,3 +370,136 @@ def project(pocket, public, next_pocket, next_public, next_abs, bins, threads=8)
     _iso().orc_project(a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, next_abs.ctypes.data, len(a[2]), bins,
                        hist.ctypes.data, threads)
     return hist
+
+
+# ── NLHE (oracle/nlhe.hpp) ─────────────────────────────────────────────────────────────────────────
+NLHE_PROBE = np.dtype([("pot", "<i2"), ("to_call", "<i2"), ("to_raise", "<i2"), ("to_shove", "<i2"),
+                       ("stack", "<i2", 2), ("stake", "<i2", 2), ("spent", "<i2", 2), ("street", "i1"), ("turn", "i1"),
+                       ("applied_kind", "u1"), ("pad", "u1"), ("applied_chips", "<i2"), ("abs", "<u2"), ("flags", "<u4"),
+                       ("subgame", "<u8"), ("choices", "<u8"), ("board", "<u8"), ("hole", "<u8", 2)])
+NLHE_ROW = np.dtype([("past", "<i8"), ("choices", "<i8"), ("edge", "<i8"), ("present", "<i2"), ("pad", "<i2", 3),
+                     ("weight", "<f4"), ("regret", "<f4"), ("payoff", "<f4"), ("visits", "<i4")])
+NLHE_NODE = np.dtype([("parent", "<i4"), ("edge", "u1"), ("turn", "u1"), ("pot", "<i2"), ("abs", "<u2"), ("pad", "<u2"),
+                      ("pad1", "<u4"), ("subgame", "<u8"), ("choices", "<u8"), ("payoff0", "<f4"), ("pad2", "<i4")])
+NLHE_FLAGS = {"must_post": 1, "must_stop": 2, "must_deal": 4, "is_everyone_alright": 8, "is_everyone_calling": 16,
+              "is_everyone_touched": 32, "is_everyone_matched": 64, "is_everyone_folding": 128, "is_everyone_shoving": 256,
+              "may_fold": 512, "may_call": 1024, "may_check": 2048, "may_raise": 4096, "may_shove": 8192}
+NLHE_KINDS = {"Draw": 0, "Fold": 1, "Call": 2, "Check": 3, "Raise": 4, "Shove": 5}
+NLHE_EDGES = {"Draw": 1, "Fold": 2, "Check": 3, "Call": 4, "Shove": 5}
+NLHE_OPENS = [2, 3, 4, 5]
+NLHE_RAISES = [(1, 4), (1, 3), (1, 2), (2, 3), (3, 4), (1, 1), (5, 4), (3, 2), (2, 1), (3, 1)]
+_nl = None
+
+
+def nlhe_edge(name, *args):
+    """Edge → u8 (kicker/src/edge.rs:117-135): Open(n) → 6+idx, Raise(n, d) → 10+idx."""
+    if name == "Open":
+        return 6 + NLHE_OPENS.index(args[0])
+    if name == "Raise":
+        return 10 + NLHE_RAISES.index(tuple(args))
+    return NLHE_EDGES[name]
+
+
+def nlhe_path(edges):
+    p = 0
+    for i, e in enumerate(edges[:12]):
+        p |= e << (5 * i)
+    return p
+
+
+def nlhe_unpath(p):
+    out = []
+    while p & 0x1F:
+        out.append(p & 0x1F)
+        p >>= 5
+    return out
+
+
+def _nlhe():
+    global _nl
+    if _nl is None:
+        l = lib()
+        vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
+        l.orc_nlhe_script.argtypes = [u64, u32, u32, i32, vp, vp, i32, vp, vp, vp]
+        l.orc_nlhe_aggression.argtypes = [u64]
+        l.orc_nlhe_path_push.restype = u64
+        l.orc_nlhe_path_push.argtypes = [u64, i32]
+        l.orc_nlhe_raises.argtypes = [i32, i32, vp]
+        l.orc_nlhe_into_chips.argtypes = [i32, i32]
+        l.orc_nlhe_default_regret.restype = ctypes.c_float
+        l.orc_nlhe_default_regret.argtypes = [i32]
+        l.orc_nlhe_deck_draw.argtypes = [ctypes.POINTER(u64), u32]
+        l.orc_nlhe_abstraction.restype = ctypes.c_uint16
+        l.orc_nlhe_abstraction.argtypes = [u64, u64]
+        l.orc_nlhe_showdown.argtypes = [i32, vp, vp, vp, vp]
+        l.orc_nlhe_create.restype = vp
+        l.orc_nlhe_create.argtypes = [u64, i32, i32, i32, i32, i32]
+        l.orc_nlhe_destroy.argtypes = [vp]
+        l.orc_nlhe_set_hyper.argtypes = [vp, vp, u32]
+        l.orc_nlhe_step.argtypes = [vp, u64]
+        l.orc_nlhe_counters.argtypes = [vp, vp]
+        l.orc_nlhe_export.restype = u64
+        l.orc_nlhe_export.argtypes = [vp, vp, u64]
+        l.orc_nlhe_tree.argtypes = [vp, i32, vp, i32]
+        _nl = l
+    return _nl
+
+
+def nlhe_script(steps, seed=0, epoch=0, tree=0, snap=False):
+    """steps: list of ("Call", 1) / ("Check",) / ("Draw",) / ("Raise", None) (None = the legal amount) / ("Edge", code).
+    Returns (probes[n+1], won[2] or None).  Raises ValueError when a step is not `is_allowed`."""
+    kinds = np.array([16 + s[1] if s[0] == "Edge" else NLHE_KINDS[s[0]] for s in steps], dtype=np.int32)
+    chips = np.array([-1 if (s[0] == "Edge" or len(s) < 2 or s[1] is None) else s[1] for s in steps], dtype=np.int32)
+    out = np.zeros(len(steps) + 1, dtype=NLHE_PROBE)
+    won = np.full(2, -32768, dtype=np.int16)
+    reward = np.zeros(2, dtype=np.int16)
+    rc = _nlhe().orc_nlhe_script(seed, epoch, tree, len(steps), kinds.ctypes.data, chips.ctypes.data, 1 if snap else 0,
+                                 out.ctypes.data, won.ctypes.data, reward.ctypes.data)
+    if rc < 0:
+        raise ValueError(f"step {-rc - 1} {steps[-rc - 1]} is not allowed")
+    return out, (None if won[0] == -32768 else (won.copy(), reward.copy()))
+
+
+class OracleNlhe:
+    def __init__(self, seed=0, batch=128, threads=1, regret="LinearRegret", weight="LinearWeight", sampling="PluribusSampling",
+                 hyper=None, warmup=None):
+        self._l = _nlhe()
+        self._h = self._l.orc_nlhe_create(seed, batch, threads, REGRETS[regret], WEIGHTS[weight], SAMPLERS[sampling])
+        if hyper is not None or warmup is not None:
+            f = np.array(hyper if hyper is not None else [1.0, 2.0, 0.05, -3e5, 0.05], dtype=np.float32)
+            self._l.orc_nlhe_set_hyper(self._h, f.ctypes.data, 16384 if warmup is None else warmup)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.orc_nlhe_destroy(self._h)
+            self._h = None
+
+    def step(self, n=1):
+        self._l.orc_nlhe_step(self._h, n)
+
+    def counters(self):
+        c = np.zeros(5, dtype=np.uint64)
+        self._l.orc_nlhe_counters(self._h, c.ctypes.data)
+        return dict(zip(("epochs", "nodes", "infos", "updates", "rows"), (int(x) for x in c)))
+
+    def export(self):
+        n = self._l.orc_nlhe_export(self._h, None, 0)
+        out = np.zeros(n, dtype=NLHE_ROW)
+        self._l.orc_nlhe_export(self._h, out.ctypes.data, n)
+        return out
+
+    def tree(self, tree, cap=1 << 16):
+        out = np.zeros(cap, dtype=NLHE_NODE)
+        n = self._l.orc_nlhe_tree(self._h, tree, out.ctypes.data, cap)
+        return out[:n]
+
+
+def nlhe_showdown(ledger):
+    """ledger: list of (risked, status 'P'|'S'|'F', packed strength) → rewards (kicker/src/showdown.rs)."""
+    n = len(ledger)
+    risked = np.array([x[0] for x in ledger], dtype=np.int16)
+    status = np.array(["PSF".index(x[1]) for x in ledger], dtype=np.uint8)
+    strength = np.array([x[2] for x in ledger], dtype=np.uint32)
+    reward = np.zeros(n, dtype=np.int16)
+    _nlhe().orc_nlhe_showdown(n, risked.ctypes.data, status.ctypes.data, strength.ctypes.data, reward.ctypes.data)
+    return reward.tolist()
