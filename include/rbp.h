@@ -127,6 +127,64 @@ int rbp_solver_sample(rbp_solver_t* s);                                   /* K1 
 int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes); /* this rank's partial sums (device) */
 int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size); /* K2 over all ranks  */
 
+/* ─────────────────────────────── MCCFR: heads-up no-limit hold'em blueprint ─────────────────────────────── */
+
+/* `Nlhe<R,W,S>` (crates/nlhe/src/solver.rs:11 `mccfr!(Nlhe, NlheEncoder, NlheTurn, NlheEdge, NlheGame, NlheInfo, 128)`;
+ * `Flagship` = LinearRegret + LinearWeight + PluribusSampling, crates/nlhe/src/lib.rs:86-90) with `batch_size()` = batch.
+ * The game plug-in is compiled in: `kicker::Game` heads-up (STACK 200, blinds 1/2, crates/kicker/src/game.rs),
+ * the Pluribus action grid (crates/pokerkit/src/lib.rs:60-160), `NlheGame::apply` with snapping
+ * (crates/nlhe/src/game.rs:35-55), `NlheInfo` = (current-street subgame Path, choices Path, Abstraction)
+ * (crates/nlhe/src/info.rs:141-160).  The profile is a device-resident open-addressing table of
+ * `table_slots` (power of two) infosets x up to 10 edges (replaces HashMap<NlheInfo, HashMap<NlheEdge, Encounter>>).
+ * RNG contract additions to rbp_philox4x32_10's: hole cards = Philox(epoch, tree, 0xFFFFFFFF, tag 1) words 0..3
+ * through Deck::draw (crates/deuce/src/deck.rs:28-43, its bias kept); board cards = Philox(epoch, tree,
+ * lo32(hist), tag 4), hist = running mix64 hash of the edges applied since the root; node draws use
+ * info word = lo32(mix64(subgame ^ mix64(choices ^ mix64(abstraction)))).
+ * Abstraction lookup (`NlheEncoder::abstraction`, crates/nlhe/src/encoder.rs:30-35): synthetic until a table is
+ * installed — bucket = mix64(canonical pocket * 0x9E3779B97F4A7C15 ^ mix64(canonical public)) mod {169,256,256,101},
+ * Abstraction = street << 8 | bucket (crates/kicker/src/abstraction.rs:15-60). */
+typedef struct rbp_nlhe rbp_nlhe_t;
+int rbp_nlhe_create(int regret, int weight, int sampling, int batch, uint64_t seed, const rbp_hyper_t* hyper /* NULL = defaults */,
+                    uint64_t table_slots, int max_nodes_per_tree, int device, rbp_nlhe_t** out);
+void rbp_nlhe_destroy(rbp_nlhe_t* s);
+int rbp_nlhe_set_world(rbp_nlhe_t* s, int world_rank, int world_size);
+int rbp_nlhe_set_stream(rbp_nlhe_t* s, void* cuda_stream);
+/* `Solver::step` x n (crates/mccfr/src/solver/solver.rs:96-105): sample `batch` trees, Decisions per walker infoset,
+ * fold in tree order (one schedule application per Decisions), advance the epoch */
+int rbp_nlhe_step(rbp_nlhe_t* s, uint64_t n_epochs);
+/* rbp_nlhe_step with CUDA-event timing per phase: ms[0] total, [1] sample+value kernel, [2] resolve+sort, [3] fold */
+int rbp_nlhe_step_timed(rbp_nlhe_t* s, uint64_t n_epochs, int flush_l2, float ms[4]);
+/* out[0] epochs, [1] nodes, [2] Decisions ("infos"), [3] infoset-action regret updates, [4] table rows in use,
+ * [5] update records of the last epoch, [6] largest tree of the run (nodes), [7] reserved */
+int rbp_nlhe_counters(rbp_nlhe_t* s, uint64_t out[8]);
+/* One row of the reference's blueprint table (crates/nlhe/src/profile.rs:143-160: past, present, choices, edge, weight,
+ * regret, payoff, visits) */
+typedef struct {
+    int64_t past;    /* i64::from(info.subgame()) — Path, 5 bits per edge, first edge lowest (crates/kicker/src/path.rs) */
+    int64_t choices; /* i64::from(info.choices()) */
+    int64_t edge;    /* u8 code of the edge (crates/kicker/src/edge.rs:117-135) */
+    int16_t present; /* i16::from(info.bucket()) — Abstraction */
+    int16_t pad[3];
+    rbp_encounter_t row;
+} rbp_nlhe_row_t;
+/* rows sorted by (past, present, choices, position of edge in choices); cap = capacity of `rows` (NULL to count) */
+int rbp_nlhe_export(rbp_nlhe_t* s, rbp_nlhe_row_t* rows, uint64_t cap, uint64_t* n_rows);
+int rbp_nlhe_import(rbp_nlhe_t* s, const rbp_nlhe_row_t* rows, uint64_t n_rows, uint64_t epochs);
+/* multi-GPU exchange (one process per GPU; the library does not link a collective library): after rbp_nlhe_sample
+ * this rank's update records sit in a device buffer (`words` 32-bit words per record, `count` of them); the host
+ * all-gathers them and hands the concatenation (any rank order: the fold sorts by (infoset, tree)) to
+ * rbp_nlhe_fold_records, which advances the epoch. */
+int rbp_nlhe_sample(rbp_nlhe_t* s);
+int rbp_nlhe_records(rbp_nlhe_t* s, void** device_ptr, uint64_t* count, uint64_t* capacity, int* words_per_record);
+int rbp_nlhe_fold_records(rbp_nlhe_t* s, const void* device_records, uint64_t count);
+/* test hook: tree `tree` of the CURRENT epoch as the sampler builds it — per node (preorder, children in choices order)
+ * depth, kind (0 walker 1 opponent 2 chance 3 terminal), action index, policy p, sampling q, terminal payoff */
+typedef struct {
+    uint8_t depth, kind, act, pad;
+    float p, q, payoff;
+} rbp_nlhe_node_t;
+int rbp_nlhe_debug_tree(rbp_nlhe_t* s, int tree, rbp_nlhe_node_t* out, int cap, int* n_nodes);
+
 /* ─────────────────────────────── deuce: hand strength and river equity ─────────────────────────────── */
 
 /* `Strength::from(Hand)` (crates/deuce/src/strength.rs:19-31 → evaluator.rs:39-177) for a batch of 52-bit hands

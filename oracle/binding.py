@@ -441,6 +441,7 @@ def _nlhe():
         l.orc_nlhe_export.restype = u64
         l.orc_nlhe_export.argtypes = [vp, vp, u64]
         l.orc_nlhe_tree.argtypes = [vp, i32, vp, i32]
+        l.orc_nlhe_tree_preorder.argtypes = [vp, i32, vp, i32]
         _nl = l
     return _nl
 
@@ -487,6 +488,12 @@ class OracleNlhe:
         out = np.zeros(n, dtype=NLHE_ROW)
         self._l.orc_nlhe_export(self._h, out.ctypes.data, n)
         return out
+
+    def tree_preorder(self, tree, cap=1 << 16):
+        dt = np.dtype([("depth", "u1"), ("kind", "u1"), ("act", "u1"), ("pad", "u1"), ("p", "<f4"), ("q", "<f4"), ("payoff", "<f4")])
+        out = np.zeros(cap, dtype=dt)
+        n = self._l.orc_nlhe_tree_preorder(self._h, tree, out.ctypes.data, cap)
+        return out[:n]
 
     def tree(self, tree, cap=1 << 16):
         out = np.zeros(cap, dtype=NLHE_NODE)

@@ -177,4 +177,41 @@ int orc_nlhe_tree(nlhe::Solver* s, int tree, OrcNlheNode* out, int cap) {
     return n;
 }
 
+// the same tree in the device builder's layout: preorder with children in choices() order; per node depth, kind
+// (0 walker 1 opponent 2 chance 3 terminal), action index in the parent's choices, policy p / sampling q of the incoming
+// edge (flow.rs:20-44), terminal payoff for the walker
+struct OrcNlhePre { uint8_t depth, kind, act, pad; float p, q, payoff; };
+int orc_nlhe_tree_preorder(nlhe::Solver* s, int tree, OrcNlhePre* out, int cap) {
+    const nlhe::Solver::TreeN t = s->build(tree);
+    const int walker = s->walker();
+    int n = 0;
+    struct Item { int node, depth; };
+    std::vector<Item> stack{{0, 0}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const Game& g = t.game[it.node].game;
+        const int turn = g.turn();
+        OrcNlhePre o{(uint8_t)it.depth, (uint8_t)(turn == Game::T_TERMINAL ? 3 : (turn == Game::T_CHANCE ? 2 : (turn == walker ? 0 : 1))), 0, 0, 1.0f, 1.0f, 0.0f};
+        if (turn == Game::T_TERMINAL) o.payoff = payoff(t.game[it.node], walker);
+        const int par = t.parent[it.node];
+        if (par >= 0) {
+            const int pt = t.game[par].game.turn();
+            if (pt < 2) {
+                const View v = s->view(t.info[par]);
+                const int a = nlhe::Solver::act_of(v, t.incoming[it.node]);
+                o.act = (uint8_t)a;
+                o.p = v.r[a] / v.rd;
+                if (pt != walker) o.q = v.sw[a] / v.z;
+            }
+        }
+        if (n < cap) out[n] = o;
+        ++n;
+        std::vector<int> kids;
+        for (int c = t.head[it.node]; c >= 0; c = t.next[c]) kids.push_back(c);
+        for (int k = (int)kids.size() - 1; k >= 0; --k) stack.push_back(Item{kids[k], it.depth + 1});
+    }
+    return n;
+}
+
 }  // extern "C"

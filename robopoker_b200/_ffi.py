@@ -103,6 +103,20 @@ def load_library():
     l.rbp_isoset_river_buckets.argtypes = [vp]
     l.rbp_isoset_project.argtypes = [vp, vp, i32, i64, i64, vp, P(u64)]
     l.rbp_canonical_batch.argtypes = [vp, vp, i64, vp, vp, vp]
+    l.rbp_nlhe_create.argtypes = [i32, i32, i32, i32, u64, P(HyperC), u64, i32, i32, P(vp)]
+    l.rbp_nlhe_destroy.argtypes = [vp]
+    l.rbp_nlhe_destroy.restype = None
+    l.rbp_nlhe_set_world.argtypes = [vp, i32, i32]
+    l.rbp_nlhe_set_stream.argtypes = [vp, vp]
+    l.rbp_nlhe_step.argtypes = [vp, u64]
+    l.rbp_nlhe_step_timed.argtypes = [vp, u64, i32, P(ctypes.c_float)]
+    l.rbp_nlhe_counters.argtypes = [vp, P(u64)]
+    l.rbp_nlhe_export.argtypes = [vp, vp, u64, P(u64)]
+    l.rbp_nlhe_import.argtypes = [vp, vp, u64, u64]
+    l.rbp_nlhe_sample.argtypes = [vp]
+    l.rbp_nlhe_records.argtypes = [vp, P(vp), P(u64), P(u64), P(i32)]
+    l.rbp_nlhe_fold_records.argtypes = [vp, vp, u64]
+    l.rbp_nlhe_debug_tree.argtypes = [vp, i32, vp, i32, P(i32)]
     _lib = l
     return l
 

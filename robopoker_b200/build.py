@@ -21,6 +21,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 SOURCES = {
     "flat_game.cpp": ["-Xcompiler", "-ffp-contract=off"],
     "mccfr.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
+    "nlhe.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
     "deuce.cu": ["-fmad=false"],
     "iso.cu": ["-fmad=false"],
     "lloyd_w1.cu": ["-fmad=false"],

@@ -9,72 +9,10 @@
 // category is a short decision chain over those masks.  Packed result keeps the reference's derived `Ord`
 // (ranking.rs:33-44 — FullHouse < Flush in the default build, as written):
 //   bits 24-27 tag | 20-23 first rank | 16-19 second rank | 0-12 kicker rank bits.
-#include "common.cuh"
+#include "cards.cuh"
 
 namespace rbp {
 
-__host__ __device__ __forceinline__ uint32_t gather_nibbles(uint64_t x) {  // bit 4i -> bit i, i < 16
-    x &= 0x1111111111111111ull;
-    x = (x | (x >> 3)) & 0x0303030303030303ull;
-    x = (x | (x >> 6)) & 0x000F000F000F000Full;
-    x = (x | (x >> 12)) & 0x000000FF000000FFull;
-    x = (x | (x >> 24)) & 0xFFFFull;
-    return (uint32_t)x;
-}
-__device__ __forceinline__ int msb(uint32_t v) { return 31 - __clz(v); }
-__device__ __forceinline__ uint32_t top_n(uint32_t k, int n) {  // evaluator.rs:51-68: drop low ranks until n remain
-    int c = __popc(k);
-    while (c > n) { k &= k - 1; --c; }
-    return k;
-}
-__device__ __forceinline__ int straight_top(uint32_t ranks) {  // evaluator.rs:114-130
-    uint32_t b = ranks & (ranks << 1);
-    b &= b << 2;            // runs of 4
-    b &= ranks << 4;        // runs of 5, marked at the top rank
-    b &= 0x1FFFu;
-    if (b) return msb(b);
-    return (ranks & 0x100Fu) == 0x100Fu ? 3 : -1;  // wheel -> Five
-}
-
-__device__ __forceinline__ uint32_t strength_of(uint64_t h) {
-    h &= 0x000FFFFFFFFFFFFFull;
-    // per-rank counts (nibble = 0..4)
-    uint64_t c = (h & 0x5555555555555555ull) + ((h >> 1) & 0x5555555555555555ull);
-    c = (c & 0x3333333333333333ull) + ((c >> 2) & 0x3333333333333333ull);
-    const uint32_t m1 = gather_nibbles(c | (c >> 1) | (c >> 2));
-    const uint32_t m2 = gather_nibbles((c >> 1) | (c >> 2));
-    const uint32_t m3 = gather_nibbles((c >> 2) | ((c >> 1) & c));
-    const uint32_t m4 = gather_nibbles(c >> 2);
-    // first suit (C,D,H,S) holding >= 5 cards (evaluator.rs:138-148); at most one exists for <= 9 cards
-    int suit = -1;
-#pragma unroll
-    for (int s = 3; s >= 0; --s)
-        if (__popcll(h & (0x0001111111111111ull << s)) >= 5) suit = s;
-    uint32_t suited = 0;
-    if (suit >= 0) {
-        suited = gather_nibbles(h >> suit);
-        const int sf = straight_top(suited);
-        if (sf >= 0) return 8u << 24 | (uint32_t)sf << 20;                                    // StraightFlush
-    }
-    if (m4) { const int q = msb(m4); return 7u << 24 | (uint32_t)q << 20 | top_n(m1 & ~(1u << q), 1); }  // FourOAK
-    const int t = m3 ? msb(m3) : -1;
-    if (t >= 0) {
-        const uint32_t rest = m2 & ~(1u << t);
-        if (rest) return 5u << 24 | (uint32_t)t << 20 | (uint32_t)msb(rest) << 16;             // FullHouse
-    }
-    if (suit >= 0) return 6u << 24 | (uint32_t)msb(suited) << 20;                              // Flush(top rank only)
-    const int st = straight_top(m1);
-    if (st >= 0) return 4u << 24 | (uint32_t)st << 20;                                         // Straight
-    if (t >= 0) return 3u << 24 | (uint32_t)t << 20 | top_n(m1 & ~(1u << t), 2);               // ThreeOAK
-    if (m2) {
-        const int hi = msb(m2);
-        const uint32_t rest = m2 & ~(1u << hi);
-        if (rest) { const int lo = msb(rest); return 2u << 24 | (uint32_t)hi << 20 | (uint32_t)lo << 16 | top_n(m1 & ~(1u << hi) & ~(1u << lo), 1); }
-        return 1u << 24 | (uint32_t)hi << 20 | top_n(m1 & ~(1u << hi), 3);                     // OnePair
-    }
-    const int h1 = msb(m1);
-    return (uint32_t)h1 << 20 | top_n(m1 & ~(1u << h1), 4);                                    // HighCard
-}
 
 __global__ void __launch_bounds__(256) eval_kernel(const uint64_t* __restrict__ hands, int64_t n, uint32_t* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

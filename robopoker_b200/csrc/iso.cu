@@ -16,48 +16,12 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "cards.cuh"
 
 namespace rbp {
 
-__device__ __forceinline__ uint32_t suit_key(uint64_t pocket, uint64_t pub, int s) {  // permutation.rs:40-54 (without the suit tiebreak)
-    const uint64_t m = 0x0001111111111111ull << s;
-    const uint64_t p = pocket & m, b = pub & m;
-    const uint32_t pmin = p ? (uint32_t)((__ffsll((long long)p) - 1) >> 2) + 1u : 0u;   // Option<Rank>: None < Some
-    const uint32_t bmin = b ? (uint32_t)((__ffsll((long long)b) - 1) >> 2) + 1u : 0u;
-    const uint32_t pmax = p ? (uint32_t)((63 - __clzll((long long)p)) >> 2) + 1u : 0u;
-    const uint32_t bmax = b ? (uint32_t)((63 - __clzll((long long)b)) >> 2) + 1u : 0u;
-    return (uint32_t)__popcll(p) << 20 | (uint32_t)__popcll(b) << 16 | pmin << 12 | bmin << 8 | pmax << 4 | bmax;
-}
-__device__ __forceinline__ bool is_canonical(uint64_t pocket, uint64_t pub) {  // isomorphism.rs:40-44
-    const uint32_t k0 = suit_key(pocket, pub, 0), k1 = suit_key(pocket, pub, 1), k2 = suit_key(pocket, pub, 2), k3 = suit_key(pocket, pub, 3);
-    return k0 <= k1 && k1 <= k2 && k2 <= k3;  // stable sort with the suit as tiebreak leaves equal keys in place
-}
-__device__ __forceinline__ void canonicalize(uint64_t& pocket, uint64_t& pub) {  // permutation.rs:9-33,55-66
-    uint32_t k[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) k[s] = suit_key(pocket, pub, s) << 2 | (uint32_t)s;  // suit id = final tiebreak
-    int perm[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        int r = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) r += k[t] < k[s];
-        perm[s] = r;  // rank of suit s in the sorted order = its new suit
-    }
-    uint64_t np = 0, nb = 0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const uint64_t m = 0x0001111111111111ull << s;
-        const int sh = perm[s] - s;
-        const uint64_t p = pocket & m, b = pub & m;
-        np |= sh >= 0 ? p << sh : p >> -sh;
-        nb |= sh >= 0 ? b << sh : b >> -sh;
-    }
-    pocket = np; pub = nb;
-}
-
 __constant__ unsigned long long c_binom[53][6];  // C(n, k), n <= 52, k <= 5
+
 
 // t-th k-subset (colex order) of the cards not in `skip`, as a card mask
 __device__ __forceinline__ uint64_t unrank_board(unsigned long long t, int k, uint64_t skip) {
