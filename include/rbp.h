@@ -135,7 +135,9 @@ int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int worl
  * the Pluribus action grid (crates/pokerkit/src/lib.rs:60-160), `NlheGame::apply` with snapping
  * (crates/nlhe/src/game.rs:35-55), `NlheInfo` = (current-street subgame Path, choices Path, Abstraction)
  * (crates/nlhe/src/info.rs:141-160).  The profile is a device-resident open-addressing table of
- * `table_slots` (power of two) infosets x up to 10 edges (replaces HashMap<NlheInfo, HashMap<NlheEdge, Encounter>>).
+ * `table_slots` (power of two, 0 = 2^22) infosets x up to 10 edges (replaces HashMap<NlheInfo, HashMap<NlheEdge, Encounter>>).
+ * `max_nodes_per_tree`: node capacity of one epoch = batch x this (0 = automatic: 768 x batch + 16384; sampled trees
+ * average ~450 nodes, the largest seen ~3500); an epoch that exceeds a capacity fails with RBP_ERR_CAPACITY.
  * RNG contract additions to rbp_philox4x32_10's: hole cards = Philox(epoch, tree, 0xFFFFFFFF, tag 1) words 0..3
  * through Deck::draw (crates/deuce/src/deck.rs:28-43, its bias kept); board cards = Philox(epoch, tree,
  * lo32(hist), tag 4), hist = running mix64 hash of the edges applied since the root; node draws use
