@@ -27,11 +27,17 @@ def parse():
     p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--batch", type=int, default=262144, help="trees per epoch per GPU")
+    p.add_argument("--workload", default="leduc", choices=["leduc", "nlhe"],
+                   help="leduc = BASELINE.json configs[1] (default); nlhe = configs[3]: heads-up NLHE blueprint MCCFR, synthetic abstraction")
+    p.add_argument("--batch", type=int, default=None, help="trees per epoch per GPU (default: 262144 leduc, 16384 nlhe)")
+    p.add_argument("--table-slots", type=int, default=1 << 24, help="nlhe: infoset table capacity (power of two)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--fold", default="batched", choices=["ordered", "batched"],
                    help="ordered = reference Solver::step semantics (serial per row); batched = blocked delta sums (scales across GPUs)")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.batch is None:
+        a.batch = 262144 if a.workload == "leduc" else 16384
+    return a
 
 
 def workload(args, n):
@@ -117,8 +123,164 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+NLHE = ("LinearRegret", "LinearWeight", "PluribusSampling")  # `Flagship` (crates/nlhe/src/lib.rs:86-90)
+
+
+def nlhe_workload(args, n):
+    return {"workload": f"configs[3] heads-up NLHE blueprint MCCFR (Flagship: {','.join(NLHE)}), {args.batch} trees/epoch/GPU, "
+                        "ordered fold, synthetic hash abstraction 169/256/256/101 (SURVEY 8d config 4)",
+            "game": "nlhe-hu", "trees_per_epoch_per_gpu": args.batch, "global_batch": args.batch * n, "parallelism": f"trees x{n}",
+            "table_slots": args.table_slots, "l2": "flushed between steps (192 MiB write), untimed"}
+
+
+def nlhe_reference(args):
+    """The oracle's NLHE solver (C++ restatement of the reference's rayon path) on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import binding as oracle
+
+    threads = os.cpu_count() or 1
+    o = oracle.OracleNlhe(seed=args.seed, batch=args.batch, threads=threads, regret=NLHE[0], weight=NLHE[1], sampling=NLHE[2])
+    o.step(min(args.warmup, 1))
+    u0 = o.counters()["updates"]
+    t0 = time.perf_counter()
+    o.step(args.steps)
+    dt = time.perf_counter() - t0
+    val = (o.counters()["updates"] - u0) / dt
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": nlhe_workload(args, 1),
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                       "sample": f"{args.steps} epochs x {args.batch} trees, C++ restatement of the reference rayon path (Rust toolchain absent)"},
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main_nlhe(args):
+    import robopoker_b200 as rbp
+    from robopoker_b200.nlhe import Nlhe
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    l = rbp.load_library()
+    if l.rbp_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — librbp_b200 has no CPU fallback")
+    s = Nlhe(regret=NLHE[0], weight=NLHE[1], sampling=NLHE[2], batch=args.batch, seed=args.seed, table_slots=args.table_slots, device=local)
+    warm = max(args.warmup, 3)
+    phases = None
+    if world == 1:
+        s.step_timed(warm, flush_l2=True)
+        c0 = s.counters()
+        clocks = Clocks(local)
+        l0 = l.rbp_kernel_launches()
+        phases = s.step_timed(args.steps, flush_l2=True)
+        ms_total = phases[0]
+        gpu_launches = l.rbp_kernel_launches() - l0
+        clk = clocks.stop()
+        c1 = s.counters()
+        updates, nodes, records = c1["updates"] - c0["updates"], c1["nodes"] - c0["nodes"], c1["records"]
+        stepper = lambda: s.step(1)  # noqa: E731
+    else:
+        import torch
+        from robopoker_b200.distributed import ShardedNlhe
+
+        stream = torch.cuda.current_stream()
+        s.set_stream(stream.cuda_stream)
+        sh = ShardedNlhe(s, dist, device=local)
+        flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+        sh.step(warm)
+        c0 = s.counters()
+        dist.barrier(); torch.cuda.synchronize()
+        clocks = Clocks(local)
+        l0 = l.rbp_kernel_launches()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record(stream)
+            sh.step(1)  # sample -> ragged all-gather of update records (NCCL) -> resolve, sort, fold of every rank's records
+            e1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        gpu_launches = l.rbp_kernel_launches() - l0
+        clk = clocks.stop()
+        c1 = s.counters()
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        # every rank folds the whole epoch; the job's work is one epoch of world*batch trees: count it once (rank 0's fold)
+        updates, nodes, records = c1["updates"] - c0["updates"], None, c1["records"]
+        stepper = lambda: sh.step(1)  # noqa: E731
+    value = updates / (ms_total * 1e-3)
+
+    # end to end through the public call: step + telemetry read-back per step, wall clock.  The path has no per-step host
+    # input (deals come from the device-side Philox contract); the host reads the 64-byte counter block every step.
+    e_steps = max(5, min(args.steps, 50))
+    u0 = s.counters()["updates"]
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        stepper()
+        s.counters()
+    e_dt = time.perf_counter() - t0
+    e_updates = s.counters()["updates"] - u0
+    if dist:
+        import torch
+        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.item())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = None
+    if phases is not None:
+        # dominant kernel: the value kernel.  Algorithmic bytes per launch: every preorder node read once (16 B) and one
+        # 72-byte update record written per walker node — the kernel re-reads nodes once per walker ancestor from L1/L2.
+        k_s = phases[2] * 1e-3 / args.steps
+        alg = (16.0 * nodes + 72.0 * records * args.steps) / args.steps
+        roofline = {"bound": "hbm", "kernel": "nlhe_value_kernel", "achieved": alg / k_s / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": alg / k_s / 1e9 / peak, "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                    "kernel_ms": {"tree_build": phases[1] / args.steps, "value": phases[2] / args.steps,
+                                  "resolve_sort": phases[3] / args.steps, "fold": phases[4] / args.steps},
+                    "note": "divergent tree walks and serial per-infoset chains: latency-bound, reported (not claimed) against the HBM roofline (SURVEY 8d)"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": nlhe_workload(args, world), "clocks": clk,
+                "e2e": {"value": e_updates / e_dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64, "steps": e_steps,
+                        "note": "no per-step host input exists on this path (device-side deals); the host reads the counter block every step"},
+                "gpu_launches": int(gpu_launches), "roofline": roofline, "epochs": c1["epochs"] + e_steps, "table_rows": s.counters()["rows"]}
+        if world == 1:
+            from oracle import binding as oracle
+
+            threads = os.cpu_count() or 1
+            cpu_epochs = max(2, int(4.0e5 // args.batch))
+            o = oracle.OracleNlhe(seed=args.seed, batch=args.batch, threads=threads, regret=NLHE[0], weight=NLHE[1], sampling=NLHE[2])
+            o.step(1)
+            u0 = o.counters()["updates"]
+            t0 = time.perf_counter()
+            o.step(cpu_epochs)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": (o.counters()["updates"] - u0) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{cpu_epochs} epochs x {args.batch} trees in {dt:.1f}s, C++ restatement of the reference rayon path"}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "nlhe":
+        return nlhe_reference(args) if args.impl == "reference" else main_nlhe(args)
     if args.impl == "reference":
         return run_reference(args)
     import numpy as np

@@ -154,8 +154,9 @@ int rbp_nlhe_set_stream(rbp_nlhe_t* s, void* cuda_stream);
 /* `Solver::step` x n (crates/mccfr/src/solver/solver.rs:96-105): sample `batch` trees, Decisions per walker infoset,
  * fold in tree order (one schedule application per Decisions), advance the epoch */
 int rbp_nlhe_step(rbp_nlhe_t* s, uint64_t n_epochs);
-/* rbp_nlhe_step with CUDA-event timing per phase: ms[0] total, [1] sample+value kernel, [2] resolve+sort, [3] fold */
-int rbp_nlhe_step_timed(rbp_nlhe_t* s, uint64_t n_epochs, int flush_l2, float ms[4]);
+/* rbp_nlhe_step with CUDA-event timing per phase (summed over the epochs): ms[0] total, [1] tree build (level expansion,
+ * size/preorder sweeps, scatter), [2] value kernel, [3] resolve + radix sort, [4] fold */
+int rbp_nlhe_step_timed(rbp_nlhe_t* s, uint64_t n_epochs, int flush_l2, float ms[5]);
 /* out[0] epochs, [1] nodes, [2] Decisions ("infos"), [3] infoset-action regret updates, [4] table rows in use,
  * [5] update records of the last epoch, [6] largest tree of the run (nodes), [7] reserved */
 int rbp_nlhe_counters(rbp_nlhe_t* s, uint64_t out[8]);

@@ -437,6 +437,10 @@ def _nlhe():
         l.orc_nlhe_destroy.argtypes = [vp]
         l.orc_nlhe_set_hyper.argtypes = [vp, vp, u32]
         l.orc_nlhe_step.argtypes = [vp, u64]
+        l.orc_nlhe_set_world.argtypes = [vp, i32, i32]
+        l.orc_nlhe_sample.restype = u64
+        l.orc_nlhe_sample.argtypes = [vp, vp, u64]
+        l.orc_nlhe_fold.argtypes = [vp, vp, u64]
         l.orc_nlhe_counters.argtypes = [vp, vp]
         l.orc_nlhe_export.restype = u64
         l.orc_nlhe_export.argtypes = [vp, vp, u64]
@@ -488,6 +492,22 @@ class OracleNlhe:
         out = np.zeros(n, dtype=NLHE_ROW)
         self._l.orc_nlhe_export(self._h, out.ctypes.data, n)
         return out
+
+    # multi-rank exchange (robopoker_b200.distributed.ShardedNlhe on the CPU/gloo path)
+    def set_world(self, rank, world):
+        self._l.orc_nlhe_set_world(self._h, rank, world)
+
+    def sample_records(self):
+        """This rank's Decisions of the epoch as an int32 matrix [count, words]."""
+        words = self._l.orc_nlhe_dec_bytes() // 4
+        n = self._l.orc_nlhe_sample(self._h, None, 0)
+        out = np.zeros((n, words), dtype=np.int32)
+        self._l.orc_nlhe_sample(self._h, out.ctypes.data, n)
+        return out
+
+    def fold_records(self, records):
+        records = np.ascontiguousarray(records, dtype=np.int32)
+        self._l.orc_nlhe_fold(self._h, records.ctypes.data, len(records))
 
     def tree_preorder(self, tree, cap=1 << 16):
         dt = np.dtype([("depth", "u1"), ("kind", "u1"), ("act", "u1"), ("pad", "u1"), ("p", "<f4"), ("q", "<f4"), ("payoff", "<f4")])

@@ -140,6 +140,21 @@ void orc_nlhe_set_hyper(nlhe::Solver* s, const float* f5, uint32_t warmup) {
     s->hyper.temperature = f5[0]; s->hyper.smoothing = f5[1]; s->hyper.curiosity = f5[2];
     s->hyper.prune_threshold = f5[3]; s->hyper.prune_explore = f5[4]; s->hyper.prune_warmup = warmup;
 }
+void orc_nlhe_set_world(nlhe::Solver* s, int rank, int world) { s->world_rank = rank; s->world_size = world; }
+int orc_nlhe_dec_bytes() { return (int)sizeof(Dec); }
+// multi-rank exchange: this rank's Decisions as raw bytes (call with out = NULL to size), then the fold of every rank's
+uint64_t orc_nlhe_sample(nlhe::Solver* s, void* out, uint64_t cap) {
+    static thread_local std::vector<Dec> pending;
+    if (!out) { pending = s->sample_decs(); return pending.size(); }
+    const uint64_t n = std::min<uint64_t>(cap, pending.size());
+    std::memcpy(out, pending.data(), n * sizeof(Dec));
+    return n;
+}
+void orc_nlhe_fold(nlhe::Solver* s, const void* decs, uint64_t count) {
+    std::vector<Dec> v(count);
+    std::memcpy(v.data(), decs, count * sizeof(Dec));
+    s->fold_decs(v);
+}
 void orc_nlhe_step(nlhe::Solver* s, uint64_t n) { for (uint64_t i = 0; i < n; ++i) s->step(); }
 void orc_nlhe_counters(nlhe::Solver* s, uint64_t* out5) {
     out5[0] = s->epochs; out5[1] = s->nodes; out5[2] = s->infos; out5[3] = s->updates; out5[4] = s->rows.size();

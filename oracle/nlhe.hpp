@@ -25,7 +25,9 @@
 // K = 169 / 256 / 256 / 101 per street; `Abstraction` = street << 8 | bucket (kicker/src/abstraction.rs:50-56).
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -364,13 +366,14 @@ inline float payoff(const State& s, int player) {  // nlhe/src/game.rs:57-63
 // ── MCCFR over this game: same arithmetic as oracle/mccfr.hpp (flow.rs / solver.rs), sparse profile ──
 struct Row { Encounter e[kMaxEdges]; bool present[kMaxEdges]; uint8_t edges[kMaxEdges]; int n; };
 struct View { int n; uint8_t edges[kMaxEdges]; float r[kMaxEdges], rd, sw[kMaxEdges], z; };
-struct Dec { Info info; int n; bool explored[kMaxEdges]; float regret[kMaxEdges], policy[kMaxEdges], payoff; };
+struct Dec { Info info; int n; int tree; bool explored[kMaxEdges]; float regret[kMaxEdges], policy[kMaxEdges], payoff; };  // POD: also the unit ranks exchange
 
 struct Solver {
     std::unordered_map<Info, Row, InfoHash> rows;
     uint64_t epochs = 0;
     Hyper hyper;
     int regret_sched = R_LINEAR, weight_sched = W_LINEAR, sampling = S_PLURIBUS, batch = 128, threads = 1;
+    int world_rank = 0, world_size = 1;  // this handle samples tree ids [rank*batch, (rank+1)*batch) of a world_size*batch epoch
     Draw rng{0};
     uint64_t nodes = 0, infos = 0, updates = 0;
 
@@ -538,6 +541,7 @@ struct Solver {
                 for (int i = 0; i < k; ++i) { const int a = act[i]; if (!d.explored[a]) { d.explored[a] = true; d.regret[a] = 0.0f; } d.regret[a] += val[i] - ev; }
             }
             d.payoff = pay;
+            d.tree = t.id;
             out.push_back(d);
         }
     }
@@ -552,21 +556,34 @@ struct Solver {
         for (int a = 0; a < d.n; ++a) { Encounter& e = mut_row(d.info, a); e.payoff += (d.payoff - e.payoff) / (float)(e.visits + 1); }
         for (int a = 0; a < d.n; ++a) mut_row(d.info, a).visits += 1;
     }
-    void step() {
+    // solver.rs:225-240 batch: this rank's trees → Decisions (tree order, first-seen infoset order inside a tree)
+    std::vector<Dec> sample_decs() {
         int T = threads < 1 ? 1 : (threads > batch ? batch : threads);
         std::vector<std::vector<Dec>> parts(T);
         std::vector<uint64_t> nc(T, 0);
         auto work = [&](int th) {
             for (int i = (int)((int64_t)batch * th / T); i < (int)((int64_t)batch * (th + 1) / T); ++i) {
-                const TreeN t = build(i);
+                const TreeN t = build(world_rank * batch + i);
                 nc[th] += t.game.size();
                 tree_decisions(t, parts[th]);
             }
         };
         if (T == 1) work(0);
         else { std::vector<std::thread> th; for (int k = 0; k < T; ++k) th.emplace_back(work, k); for (auto& x : th) x.join(); }
-        for (int k = 0; k < T; ++k) { nodes += nc[k]; infos += parts[k].size(); for (const Dec& d : parts[k]) apply_dec(d); }
+        std::vector<Dec> all;
+        for (int k = 0; k < T; ++k) { nodes += nc[k]; all.insert(all.end(), parts[k].begin(), parts[k].end()); }
+        return all;
+    }
+    // solver.rs:96-105: every Decisions of the epoch (all ranks'), applied in global tree order
+    void fold_decs(std::vector<Dec>& decs) {
+        std::stable_sort(decs.begin(), decs.end(), [](const Dec& a, const Dec& b) { return a.tree < b.tree; });
+        infos += decs.size();
+        for (const Dec& d : decs) apply_dec(d);
         epochs += 1;
+    }
+    void step() {
+        std::vector<Dec> decs = sample_decs();
+        fold_decs(decs);
     }
 };
 

@@ -56,8 +56,8 @@ class Nlhe:
         return self.step(trees // self.batch)
 
     def step_timed(self, n=1, flush_l2=True):
-        """Returns device ms (total, sample+value, resolve+sort, fold) summed over n epochs."""
-        ms = (ctypes.c_float * 4)()
+        """Returns device ms (total, tree build, value kernel, resolve+sort, fold) summed over n epochs."""
+        ms = (ctypes.c_float * 5)()
         _ffi.check(self._lib.rbp_nlhe_step_timed(self._h, n, int(flush_l2), ms), "rbp_nlhe_step_timed")
         return tuple(ms)
 
