@@ -102,16 +102,3 @@ def test_large_batch_properties(rbp):
     keys = np.stack([rows["past"], rows["present"].astype(np.int64), rows["choices"]], axis=1)
     assert len(np.unique(keys, axis=0)) == c["rows"]
 
-
-def test_reference_builder_matches_level_builder(rbp, oracle, monkeypatch):
-    """The serial one-thread-per-tree builder (RBP_NLHE_BUILDER=dfs) and the level-synchronous one produce the same profile."""
-    monkeypatch.setenv("RBP_NLHE_BUILDER", "dfs")
-    a, o = make(rbp, oracle, 96, 21, slots=1 << 17)
-    monkeypatch.delenv("RBP_NLHE_BUILDER")
-    b, _ = make(rbp, oracle, 96, 21, slots=1 << 17)
-    trees_equal(a, o, range(0, 96, 5))
-    a.step(4), b.step(4), o.step(4)
-    rows_equal(b.profile(), o.export())
-    rows_equal(a.profile(), o.export())
-    ca, cb = a.counters(), b.counters()
-    assert {k: ca[k] for k in ("nodes", "infos", "updates", "rows")} == {k: cb[k] for k in ("nodes", "infos", "updates", "rows")}
