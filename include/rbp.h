@@ -146,6 +146,7 @@ int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int worl
  * installed — bucket = mix64(canonical pocket * 0x9E3779B97F4A7C15 ^ mix64(canonical public)) mod {169,256,256,101},
  * Abstraction = street << 8 | bucket (crates/kicker/src/abstraction.rs:15-60). */
 typedef struct rbp_nlhe rbp_nlhe_t;
+struct rbp_isoset; /* rbp_isoset_t, declared with the isomorphism entry points below */
 int rbp_nlhe_create(int regret, int weight, int sampling, int batch, uint64_t seed, const rbp_hyper_t* hyper /* NULL = defaults */,
                     uint64_t table_slots, int max_nodes_per_tree, int device, rbp_nlhe_t** out);
 void rbp_nlhe_destroy(rbp_nlhe_t* s);
@@ -173,6 +174,12 @@ typedef struct {
 /* rows sorted by (past, present, choices, position of edge in choices); cap = capacity of `rows` (NULL to count) */
 int rbp_nlhe_export(rbp_nlhe_t* s, rbp_nlhe_row_t* rows, uint64_t cap, uint64_t* n_rows);
 int rbp_nlhe_import(rbp_nlhe_t* s, const rbp_nlhe_row_t* rows, uint64_t n_rows, uint64_t epochs);
+/* `NlheEncoder(BTreeMap<Isomorphism, Abstraction>)` (crates/nlhe/src/encoder.rs:23-35; the table `Hydrate` streams from
+ * Postgres, encoder.rs:187-214): install the abstraction lookup of ONE street from a device-resident isomorphism set
+ * whose abstraction column is filled (rbp_isoset_river_buckets, or rbp_isoset_set_abstractions with the k-means
+ * assignments of that street).  Streets without a table keep the synthetic lookup.  After this call an observation that
+ * is missing from the table fails the step with RBP_ERR_STATE — the reference panics ("isomorphism not found"). */
+int rbp_nlhe_set_lookup(rbp_nlhe_t* s, struct rbp_isoset* isos);
 /* multi-GPU exchange (one process per GPU; the library does not link a collective library): after rbp_nlhe_sample
  * this rank's update records sit in a device buffer (`words` 32-bit words per record, `count` of them); the host
  * all-gathers them and hands the concatenation (any rank order: the fold sorts by (infoset, tree)) to

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "cards.cuh"
+#include "isoset.hpp"
 
 namespace rbp {
 
@@ -143,15 +144,6 @@ project_kernel(const uint64_t* __restrict__ pp, const uint64_t* __restrict__ pb,
 }  // namespace rbp
 
 using namespace rbp;
-
-struct rbp_isoset {
-    int street = 0, device = 0;
-    int64_t n = 0;
-    uint64_t* pocket = nullptr;
-    uint64_t* pub = nullptr;
-    uint8_t* abs = nullptr;  // optional abstraction column (lookup table iso → bucket)
-    bool have_abs = false;
-};
 
 namespace {
 int board_cards(int street) { return street == 0 ? 0 : street + 2; }

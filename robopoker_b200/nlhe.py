@@ -77,6 +77,11 @@ class Nlhe:
         rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
         _ffi.check(self._lib.rbp_nlhe_import(self._h, rows.ctypes.data, len(rows), epochs), "rbp_nlhe_import")
 
+    def set_lookup(self, isoset):
+        """Install one street's abstraction table (`NlheEncoder`'s BTreeMap) from a `robopoker_b200.deuce.IsoSet` whose
+        abstraction column is filled (river equity buckets, or the k-means assignments of that street)."""
+        _ffi.check(self._lib.rbp_nlhe_set_lookup(self._h, isoset._h), "rbp_nlhe_set_lookup")
+
     # multi-GPU exchange (robopoker_b200.distributed.ShardedNlhe)
     def sample(self):
         _ffi.check(self._lib.rbp_nlhe_sample(self._h), "rbp_nlhe_sample")
