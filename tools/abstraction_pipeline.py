@@ -26,6 +26,9 @@ def main():
     p.add_argument("--iters", type=int, default=32)
     p.add_argument("--flop-n", type=int, default=20000, help="flop points clustered with the Sinkhorn layer (0 = skip)")
     p.add_argument("--flop-iters", type=int, default=4)
+    p.add_argument("--blueprint-epochs", type=int, default=0,
+                   help="then train the NLHE blueprint on the clustered abstraction for this many epochs (`trainer --blueprint`)")
+    p.add_argument("--blueprint-batch", type=int, default=16384)
     args = p.parse_args()
     import numpy as np
 
@@ -51,7 +54,8 @@ def main():
         hist[off:off + len(h)] = h
         misses += m
     stage("turn_projections", t0, n=n_turn, misses=misses)
-    river.close()
+    if not args.blueprint_epochs:
+        river.close()
     t0 = time.perf_counter()
     layer = rbp.lloyd.Layer(hist, args.turn_k)
     layer.init_centroids(0)
@@ -82,6 +86,34 @@ def main():
         fl.init_bounds()
         st = [fl.step() for _ in range(args.flop_iters)]
         stage("flop_sinkhorn_kmeans_subsample", t0, n=len(sub), k=args.flop_k, iters=args.flop_iters, last_reassigned=st[-1].reassignment)
+        if args.blueprint_epochs:
+            t0 = time.perf_counter()
+            if len(sub) < len(fh):  # `Layer::lookup` for every flop isomorphism against the learned centroids
+                centroids, _ = fl.future()
+                fl.close()
+                fl = rbp.lloyd.Layer(fh, args.flop_k, metric=turn_metric)
+                fl.set_centroids(centroids)
+            flop.set_abstractions(fl.lookup().astype(np.uint8))
+            stage("flop_lookup_all", t0, n=len(fh), solves=len(fh) * args.flop_k)
+        fl.close()
+    if args.blueprint_epochs:
+        # `trainer --blueprint`: NlheEncoder's isomorphism → abstraction table is the clustering output, street by street
+        from robopoker_b200.nlhe import Nlhe
+
+        t0 = time.perf_counter()
+        solver = Nlhe(batch=args.blueprint_batch, seed=0, table_slots=1 << 24)
+        pref = rbp.deuce.IsoSet("pref")
+        pref.set_abstractions(np.arange(len(pref), dtype=np.uint8))  # preflop: one bucket per isomorphism (169)
+        for isos in (pref, flop, turn, river):
+            solver.set_lookup(isos)
+            isos.close()
+        stage("blueprint_install_lookups", t0, streets=4)
+        t0 = time.perf_counter()
+        solver.step(args.blueprint_epochs)
+        dt = time.perf_counter() - t0
+        c = solver.counters()
+        stage("blueprint_mccfr", t0, epochs=args.blueprint_epochs, trees=args.blueprint_epochs * args.blueprint_batch,
+              updates=c["updates"], updates_per_s=c["updates"] / dt, infosets=c["rows"])
 
 
 if __name__ == "__main__":
