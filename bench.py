@@ -129,7 +129,7 @@ NLHE = ("LinearRegret", "LinearWeight", "PluribusSampling")  # `Flagship` (crate
 def nlhe_workload(args, n):
     return {"workload": f"configs[3] heads-up NLHE blueprint MCCFR (Flagship: {','.join(NLHE)}), {args.batch} trees/epoch/GPU, "
                         "ordered fold, synthetic hash abstraction 169/256/256/101 (SURVEY 8d config 4)",
-            "game": "nlhe-hu", "trees_per_epoch_per_gpu": args.batch, "global_batch": args.batch * n, "parallelism": f"trees x{n}",
+            "game": "nlhe-hu", "trees_per_epoch_per_gpu": args.batch, "global_batch": args.batch * n, "parallelism": f"trees x{n}, infosets owned by hash mod {n}" if n > 1 else "trees x1",
             "table_slots": args.table_slots, "l2": "flushed between steps (192 MiB write), untimed"}
 
 
@@ -203,7 +203,7 @@ def main_nlhe(args):
         for e0, e1 in evs:
             flush.zero_()
             e0.record(stream)
-            sh.step(1)  # sample -> ragged all-gather of update records (NCCL) -> resolve, sort, fold of every rank's records
+            sh.step(1)  # sample -> records to their owner ranks (NCCL all-to-all) -> fold -> all-gather of the touched rows
             e1.record(stream)
         torch.cuda.synchronize(); dist.barrier()
         ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
@@ -213,8 +213,10 @@ def main_nlhe(args):
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        # every rank folds the whole epoch; the job's work is one epoch of world*batch trees: count it once (rank 0's fold)
-        updates, nodes, records = c1["updates"] - c0["updates"], None, c1["records"]
+        # owner-sharded fold: every rank folds the infosets it owns, so the job's updates are the sum over ranks
+        t = torch.tensor([c1["updates"] - c0["updates"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        updates, nodes, records = float(t.item()), None, c1["records"]
         stepper = lambda: sh.step(1)  # noqa: E731
     value = updates / (ms_total * 1e-3)
 
@@ -235,6 +237,9 @@ def main_nlhe(args):
         t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_dt = float(t.item())
+        t = torch.tensor([e_updates], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        e_updates = float(t.item())
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

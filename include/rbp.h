@@ -187,6 +187,14 @@ int rbp_nlhe_set_lookup(rbp_nlhe_t* s, struct rbp_isoset* isos);
 int rbp_nlhe_sample(rbp_nlhe_t* s);
 int rbp_nlhe_records(rbp_nlhe_t* s, void** device_ptr, uint64_t* count, uint64_t* capacity, int* words_per_record);
 int rbp_nlhe_fold_records(rbp_nlhe_t* s, const void* device_records, uint64_t count);
+/* Owner-sharded fold (scales the fold with the world): infosets are owned by rank hash(key) mod world.
+ *   rbp_nlhe_sample → rbp_nlhe_partition_records (this rank's records grouped by owner; counts[r] go to rank r)
+ *   → host all-to-all → rbp_nlhe_fold_records (the records this rank owns) → rbp_nlhe_touched_rows (key + 10 encounters per
+ *   touched infoset, `words` 32-bit words each) → host all-gather → rbp_nlhe_apply_rows (overwrite the replica).
+ * Every rank's table then holds the same rows as one process folding the whole epoch. */
+int rbp_nlhe_partition_records(rbp_nlhe_t* s, void** device_ptr, uint64_t* counts /* [world_size] */);
+int rbp_nlhe_touched_rows(rbp_nlhe_t* s, void** device_ptr, uint64_t* count, int* words_per_row);
+int rbp_nlhe_apply_rows(rbp_nlhe_t* s, const void* device_rows, uint64_t count);
 /* test hook: tree `tree` of the CURRENT epoch as the sampler builds it — per node (preorder, children in choices order)
  * depth, kind (0 walker 1 opponent 2 chance 3 terminal), action index, policy p, sampling q, terminal payoff */
 typedef struct {

@@ -441,6 +441,10 @@ def _nlhe():
         l.orc_nlhe_sample.restype = u64
         l.orc_nlhe_sample.argtypes = [vp, vp, u64]
         l.orc_nlhe_fold.argtypes = [vp, vp, u64]
+        l.orc_nlhe_owner.argtypes = [vp, i32]
+        l.orc_nlhe_touched.restype = u64
+        l.orc_nlhe_touched.argtypes = [vp, vp, u64]
+        l.orc_nlhe_apply_rows.argtypes = [vp, vp, u64]
         l.orc_nlhe_counters.argtypes = [vp, vp]
         l.orc_nlhe_export.restype = u64
         l.orc_nlhe_export.argtypes = [vp, vp, u64]
@@ -508,6 +512,24 @@ class OracleNlhe:
     def fold_records(self, records):
         records = np.ascontiguousarray(records, dtype=np.int32)
         self._l.orc_nlhe_fold(self._h, records.ctypes.data, len(records))
+
+    def partition_records(self, world):
+        """This rank's Decisions grouped by owner rank (hash(infoset) mod world): (int32 matrix, [count per destination])."""
+        recs = self.sample_records()
+        owners = np.array([self._l.orc_nlhe_owner(recs[i].ctypes.data, world) for i in range(len(recs))], dtype=np.int64)
+        order = np.argsort(owners, kind="stable")
+        return np.ascontiguousarray(recs[order]), [int((owners == r).sum()) for r in range(world)]
+
+    def touched_rows(self):
+        words = self._l.orc_nlhe_packed_bytes() // 4
+        n = self._l.orc_nlhe_touched(self._h, None, 0)
+        out = np.zeros((n, words), dtype=np.int32)
+        self._l.orc_nlhe_touched(self._h, out.ctypes.data, n)
+        return out
+
+    def apply_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self._l.orc_nlhe_apply_rows(self._h, rows.ctypes.data, len(rows))
 
     def tree_preorder(self, tree, cap=1 << 16):
         dt = np.dtype([("depth", "u1"), ("kind", "u1"), ("act", "u1"), ("pad", "u1"), ("p", "<f4"), ("q", "<f4"), ("payoff", "<f4")])

@@ -155,6 +155,26 @@ void orc_nlhe_fold(nlhe::Solver* s, const void* decs, uint64_t count) {
     std::memcpy(v.data(), decs, count * sizeof(Dec));
     s->fold_decs(v);
 }
+// owner-sharded exchange: owner of a Decisions' infoset, the rows the last fold touched, and their installation
+int orc_nlhe_owner(const void* dec, int world) { return (int)((InfoHash()(static_cast<const Dec*>(dec)->info) >> 40) % (uint64_t)world); }
+struct OrcNlhePacked { Info info; Row row; };
+int orc_nlhe_packed_bytes() { return (int)sizeof(OrcNlhePacked); }
+uint64_t orc_nlhe_touched(nlhe::Solver* s, void* out, uint64_t cap) {
+    if (out)
+        for (uint64_t i = 0; i < s->touched.size() && i < cap; ++i) {
+            OrcNlhePacked p{};
+            p.info = s->touched[i]; p.row = s->rows.at(s->touched[i]);
+            std::memcpy(static_cast<char*>(out) + i * sizeof(OrcNlhePacked), &p, sizeof(p));
+        }
+    return s->touched.size();
+}
+void orc_nlhe_apply_rows(nlhe::Solver* s, const void* rows, uint64_t count) {
+    for (uint64_t i = 0; i < count; ++i) {
+        OrcNlhePacked p;
+        std::memcpy(&p, static_cast<const char*>(rows) + i * sizeof(OrcNlhePacked), sizeof(p));
+        s->rows[p.info] = p.row;
+    }
+}
 void orc_nlhe_step(nlhe::Solver* s, uint64_t n) { for (uint64_t i = 0; i < n; ++i) s->step(); }
 void orc_nlhe_counters(nlhe::Solver* s, uint64_t* out5) {
     out5[0] = s->epochs; out5[1] = s->nodes; out5[2] = s->infos; out5[3] = s->updates; out5[4] = s->rows.size();

@@ -376,6 +376,7 @@ struct Solver {
     int world_rank = 0, world_size = 1;  // this handle samples tree ids [rank*batch, (rank+1)*batch) of a world_size*batch epoch
     Draw rng{0};
     uint64_t nodes = 0, infos = 0, updates = 0;
+    std::vector<Info> touched;  // infosets the last fold wrote (owner-sharded exchange: the rows a rank broadcasts)
 
     struct TreeN {
         int id;
@@ -578,7 +579,12 @@ struct Solver {
     void fold_decs(std::vector<Dec>& decs) {
         std::stable_sort(decs.begin(), decs.end(), [](const Dec& a, const Dec& b) { return a.tree < b.tree; });
         infos += decs.size();
-        for (const Dec& d : decs) apply_dec(d);
+        touched.clear();
+        std::unordered_map<Info, bool, InfoHash> seen;
+        for (const Dec& d : decs) {
+            apply_dec(d);
+            if (seen.emplace(d.info, true).second) touched.push_back(d.info);
+        }
         epochs += 1;
     }
     void step() {

@@ -115,6 +115,9 @@ def load_library():
     l.rbp_nlhe_import.argtypes = [vp, vp, u64, u64]
     l.rbp_nlhe_sample.argtypes = [vp]
     l.rbp_nlhe_set_lookup.argtypes = [vp, vp]
+    l.rbp_nlhe_partition_records.argtypes = [vp, P(vp), P(u64)]
+    l.rbp_nlhe_touched_rows.argtypes = [vp, P(vp), P(u64), P(i32)]
+    l.rbp_nlhe_apply_rows.argtypes = [vp, vp, u64]
     l.rbp_nlhe_records.argtypes = [vp, P(vp), P(u64), P(u64), P(i32)]
     l.rbp_nlhe_fold_records.argtypes = [vp, vp, u64]
     l.rbp_nlhe_debug_tree.argtypes = [vp, i32, vp, i32, P(i32)]

@@ -66,17 +66,22 @@ class ShardedSolver:
 
 class ShardedNlhe:
     """`Nlhe::step` across `world_size` ranks against replicated profile tables.  Rank r samples tree ids
-    [r*batch, (r+1)*batch) of each epoch; the ranks all-gather their update records (ragged: counts first, then the padded
-    record words) and every rank folds the whole epoch's records in (infoset, tree) order — tables stay bit-identical on
-    all ranks and equal to a single process running world_size*batch trees.
+    [r*batch, (r+1)*batch) of each epoch.  Two exchanges are implemented, both ending with tables that hold, on every
+    rank, exactly the rows of ONE process running world_size*batch trees:
 
-    `solver` is the GPU `robopoker_b200.nlhe.Nlhe` or the CPU oracle (`sample_records/fold_records` on host arrays), which
-    is how the world_size-2 gloo test exercises this class without a GPU."""
+    * "owner" (default): infosets are owned by rank hash(key) mod world.  Records go to their owner (ragged all-to-all),
+      each rank folds only what it owns — the fold's work per rank does not grow with the world — and the touched rows
+      (176 B each) are all-gathered and written into every replica.
+    * "replicated": ranks all-gather every record and each folds the whole epoch (simplest; fold work grows with world).
 
-    def __init__(self, solver, dist=None, device=None):
+    `solver` is the GPU `robopoker_b200.nlhe.Nlhe` or the CPU oracle (same method names on host arrays), which is how the
+    world_size-2 gloo tests exercise this class without a GPU."""
+
+    def __init__(self, solver, dist=None, device=None, mode="owner"):
         import torch
 
-        self.solver, self.dist, self.torch = solver, dist, torch
+        assert mode in ("owner", "replicated")
+        self.solver, self.dist, self.torch, self.mode = solver, dist, torch, mode
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.on_gpu = hasattr(solver, "records")
@@ -87,31 +92,65 @@ class ShardedNlhe:
             self.words = words
             self.local = torch.as_tensor(_DeviceWords(ptr, cap * words * 4), device=self.device).view(cap, words)
 
+    def _counts(self, mine, device):
+        """all-gather of one integer per rank."""
+        torch = self.torch
+        counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device=device))
+        return counts.tolist()
+
     def _gather(self, local, count):
         """Ragged all-gather of [count, words] int32 rows → one [total, words] tensor (rank order)."""
         torch, dist = self.torch, self.dist
         if dist is None or self.world == 1:
             return local[:count]
-        counts = torch.zeros(self.world, dtype=torch.int64, device=local.device)
-        mine = torch.tensor([count], dtype=torch.int64, device=local.device)
-        dist.all_gather_into_tensor(counts, mine)
-        counts = counts.tolist()
-        width = max(counts)
-        if local.shape[0] < width:  # host path: pad this rank's rows up to the widest shard
+        counts = self._counts(count, local.device)
+        width = max(max(counts), 1)
+        if local.shape[0] < width:  # pad this rank's rows up to the widest shard
             local = torch.cat([local, torch.zeros(width - local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)])
         padded = torch.empty(self.world * width, local.shape[1], dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(padded, local[:width].contiguous())
         return torch.cat([padded[r * width:r * width + counts[r]] for r in range(self.world)]).contiguous()
 
+    def _to_owners(self, grouped, counts):
+        """Ragged all-to-all: rows [sum(counts), words] grouped by destination rank → the rows destined to this rank."""
+        torch, dist = self.torch, self.dist
+        send = torch.tensor(counts, dtype=torch.int64, device=grouped.device)
+        recv = torch.zeros_like(send)
+        dist.all_to_all_single(recv, send)
+        recv = recv.tolist()
+        out = torch.empty(sum(recv), grouped.shape[1], dtype=grouped.dtype, device=grouped.device)
+        dist.all_to_all_single(out, grouped[:sum(counts)].contiguous(), output_split_sizes=recv, input_split_sizes=counts)
+        return out
+
     def step(self, n=1):
         torch = self.torch
         for _ in range(n):
+            owner = self.mode == "owner" and self.world > 1
             if self.on_gpu:
                 self.solver.sample()  # returns with the library stream drained
-                _, count, _, _ = self.solver.records()
-                every = self._gather(self.local, count)
-                torch.cuda.current_stream(self.device).synchronize()
-                self.solver.fold_records(every.data_ptr(), every.shape[0])
+                if owner:
+                    ptr, counts = self.solver.partition_records(self.world)
+                    grouped = torch.as_tensor(_DeviceWords(ptr, max(sum(counts), 1) * self.words * 4), device=self.device).view(-1, self.words)
+                    mine = self._to_owners(grouped, counts)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self.solver.fold_records(mine.data_ptr(), mine.shape[0])
+                    rptr, rcount, rwords = self.solver.touched_rows()
+                    rows = torch.as_tensor(_DeviceWords(rptr, max(rcount, 1) * rwords * 4), device=self.device).view(-1, rwords)
+                    every = self._gather(rows, rcount)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self.solver.apply_rows(every.data_ptr(), every.shape[0])
+                else:
+                    _, count, _, _ = self.solver.records()
+                    every = self._gather(self.local, count)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self.solver.fold_records(every.data_ptr(), every.shape[0])
+            elif owner:
+                grouped, counts = self.solver.partition_records(self.world)
+                mine = self._to_owners(torch.from_numpy(grouped), counts)
+                self.solver.fold_records(mine.numpy())
+                rows = torch.from_numpy(self.solver.touched_rows())
+                self.solver.apply_rows(self._gather(rows, rows.shape[0]).numpy())
             else:
                 mine = torch.from_numpy(self.solver.sample_records())
                 every = self._gather(mine, mine.shape[0])

@@ -94,6 +94,20 @@ class Nlhe:
     def fold_records(self, dev_ptr, count):
         _ffi.check(self._lib.rbp_nlhe_fold_records(self._h, ctypes.c_void_p(dev_ptr), count), "rbp_nlhe_fold_records")
 
+    def partition_records(self, world):
+        """This rank's records grouped by owner rank: (device pointer, [count per destination rank])."""
+        p, counts = ctypes.c_void_p(), (ctypes.c_uint64 * world)()
+        _ffi.check(self._lib.rbp_nlhe_partition_records(self._h, ctypes.byref(p), counts), "rbp_nlhe_partition_records")
+        return p.value, [int(c) for c in counts]
+
+    def touched_rows(self):
+        p, n, w = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int()
+        _ffi.check(self._lib.rbp_nlhe_touched_rows(self._h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(w)), "rbp_nlhe_touched_rows")
+        return p.value, n.value, w.value
+
+    def apply_rows(self, dev_ptr, count):
+        _ffi.check(self._lib.rbp_nlhe_apply_rows(self._h, ctypes.c_void_p(dev_ptr), count), "rbp_nlhe_apply_rows")
+
     def debug_tree(self, tree, cap=16384):
         out = np.zeros(cap, dtype=NODE_DTYPE)
         n = ctypes.c_int()

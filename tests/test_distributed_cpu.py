@@ -120,7 +120,7 @@ def test_two_rank_kmeans_allreduce_matches_single_process(tmp_path, oracle):
         assert np.array_equal(np.load(tmp_path / f"kdrift{r}.npy").view(np.uint32), drifts.view(np.uint32))
 
 
-def _nlhe_worker(rank, world, port, batch, epochs, out_dir):
+def _nlhe_worker(rank, world, port, batch, epochs, out_dir, mode="replicated"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
@@ -129,7 +129,7 @@ def _nlhe_worker(rank, world, port, batch, epochs, out_dir):
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     s = oracle.OracleNlhe(seed=13, batch=batch)
-    ShardedNlhe(s, dist).step(epochs)
+    ShardedNlhe(s, dist, mode=mode).step(epochs)
     np.save(os.path.join(out_dir, f"nlhe{rank}.npy"), s.export())
     dist.barrier()
     dist.destroy_process_group()
@@ -141,6 +141,20 @@ def test_two_rank_gloo_nlhe_records_exchange(tmp_path, oracle):
 
     world, batch, epochs = 2, 24, 3
     mp.spawn(_nlhe_worker, args=(world, _free_port(), batch, epochs, str(tmp_path)), nprocs=world, join=True)
+    rows = [np.load(tmp_path / f"nlhe{r}.npy") for r in range(world)]
+    assert rows[0].tobytes() == rows[1].tobytes()
+    whole = oracle.OracleNlhe(seed=13, batch=world * batch)
+    whole.step(epochs)
+    assert whole.export().tobytes() == rows[0].tobytes() and len(rows[0]) > 1000
+
+
+def test_two_rank_gloo_nlhe_owner_sharded_fold(tmp_path, oracle):
+    """Owner-sharded exchange (all-to-all of records to the infoset's owner, fold, all-gather of the touched rows): both
+    replicas end identical to ONE process running 2*batch trees."""
+    import torch.multiprocessing as mp
+
+    world, batch, epochs = 2, 24, 3
+    mp.spawn(_nlhe_worker, args=(world, _free_port(), batch, epochs, str(tmp_path), "owner"), nprocs=world, join=True)
     rows = [np.load(tmp_path / f"nlhe{r}.npy") for r in range(world)]
     assert rows[0].tobytes() == rows[1].tobytes()
     whole = oracle.OracleNlhe(seed=13, batch=world * batch)

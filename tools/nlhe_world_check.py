@@ -14,18 +14,23 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl")
 batch, epochs = 4096, 4
-s = Nlhe(batch=batch, seed=17, table_slots=1 << 22, device=local)
-s.set_stream(torch.cuda.current_stream().cuda_stream)
-ShardedNlhe(s, dist, device=local).step(epochs)
-rows = s.profile()
-digest = torch.tensor([int.from_bytes(__import__("hashlib").sha256(rows.tobytes()).digest()[:7], "little")], device="cuda")
-every = [torch.zeros_like(digest) for _ in range(world)]
-dist.all_gather(every, digest)
-same = all(int(e.item()) == int(every[0].item()) for e in every)
-if rank == 0:
-    whole = Nlhe(batch=batch * world, seed=17, table_slots=1 << 22, device=local)
-    whole.step(epochs)
-    ref = whole.profile()
-    print("ranks identical:", same, "| equal to one process with", batch * world, "trees:", ref.tobytes() == rows.tobytes(), "| rows", len(rows))
-dist.barrier()
+whole = None
+for mode in ("owner", "replicated"):
+    s = Nlhe(batch=batch, seed=17, table_slots=1 << 22, device=local)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    ShardedNlhe(s, dist, device=local, mode=mode).step(epochs)
+    rows = s.profile()
+    digest = torch.tensor([int.from_bytes(__import__("hashlib").sha256(rows.tobytes()).digest()[:7], "little")], device="cuda")
+    every = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(every, digest)
+    same = all(int(e.item()) == int(every[0].item()) for e in every)
+    if rank == 0:
+        if whole is None:
+            w = Nlhe(batch=batch * world, seed=17, table_slots=1 << 22, device=local)
+            w.step(epochs)
+            whole = w.profile()
+            w.close()
+        print(mode, "| ranks identical:", same, "| equal to one process with", batch * world, "trees:", whole.tobytes() == rows.tobytes(), "| rows", len(rows), flush=True)
+    s.close()
+    dist.barrier()
 dist.destroy_process_group()
