@@ -58,6 +58,21 @@ __host__ __device__ __forceinline__ uint32_t draw_range(uint32_t r, uint32_t n) 
 }
 __host__ __device__ __forceinline__ float draw_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
+// (shared by the ordered folds of mccfr.cu and nlhe.cu; `rbp_selftest_div_by_count` checks it on the device)
+// a / b for b = (float)(visits + 1), with the reciprocal prepared off the dependent chain.
+// rb = RN(1/b); q = RN(a*rb); r = a - b*q (exact, FMA); q' = RN(q + r*rb) is the correctly rounded quotient
+// (Markstein's theorem) whenever no intermediate under/overflows and b's significand is not all ones — both
+// guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
+__device__ __forceinline__ float div_by_count(float a, float b, float rb) {
+    // exponent of a within [2^-64, 2^63] (zero takes the slow path too), evaluated beside the FMA chain
+    const bool safe = ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (__float_as_uint(a) == 0u)) & ((__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu);
+    const float q = a * rb;
+    const float r = __fmaf_rn(-b, q, a);
+    const float fast = __fmaf_rn(r, rb, q);
+    if (__builtin_expect(!safe, 0)) return a / b;
+    return fast;
+}
+
 constexpr float kEps = 1.17549435e-38f;  // pokerkit/src/lib.rs:204 EPSILON = f32::MIN_POSITIVE
 
 }  // namespace rbp

@@ -402,20 +402,6 @@ __device__ __forceinline__ float regret_gain(const RegretConst& c, float net, fl
     return fmax_ref(acc, c.floor);
 }
 
-// a / b for b = (float)(visits + 1), with the reciprocal prepared off the dependent chain.
-// rb = RN(1/b); q = RN(a*rb); r = a - b*q (exact, FMA); q' = RN(q + r*rb) is the correctly rounded quotient
-// (Markstein's theorem) whenever no intermediate under/overflows and b's significand is not all ones — both
-// guarded, falling back to IEEE division.  tests/test_mccfr_gpu.py checks it against `/` exhaustively in b.
-__device__ __forceinline__ float div_by_count(float a, float b, float rb) {
-    // exponent of a within [2^-64, 2^63] (zero takes the slow path too), evaluated beside the FMA chain
-    const bool safe = ((((__float_as_uint(a) >> 23 & 0xFFu) - 63u) < 128u) | (__float_as_uint(a) == 0u)) & ((__float_as_uint(b) & 0x7FFFFFu) != 0x7FFFFFu);
-    const float q = a * rb;
-    const float r = __fmaf_rn(-b, q, a);
-    const float fast = __fmaf_rn(r, rb, q);
-    if (__builtin_expect(!safe, 0)) return a / b;
-    return fast;
-}
-
 template <int RS, int WS, bool MASKED>
 __global__ void __launch_bounds__(96)
 mccfr_fold_kernel(DevGame g, rbp_encounter_t* __restrict__ table, Scratch sc, EpochArgs ep) {
