@@ -180,6 +180,9 @@ int rbp_nlhe_import(rbp_nlhe_t* s, const rbp_nlhe_row_t* rows, uint64_t n_rows, 
  * assignments of that street).  Streets without a table keep the synthetic lookup.  After this call an observation that
  * is missing from the table fails the step with RBP_ERR_STATE — the reference panics ("isomorphism not found"). */
 int rbp_nlhe_set_lookup(rbp_nlhe_t* s, struct rbp_isoset* isos);
+/* the same from host rows in the reference's `isomorphism` table format (obs = i64::from(Isomorphism), abs =
+ * i16::from(Abstraction)); one call per street with every row of that street */
+int rbp_nlhe_set_lookup_rows(rbp_nlhe_t* s, const int64_t* obs, const int16_t* abs, int64_t n);
 /* multi-GPU exchange (one process per GPU; the library does not link a collective library): after rbp_nlhe_sample
  * this rank's update records sit in a device buffer (`words` 32-bit words per record, `count` of them); the host
  * all-gathers them and hands the concatenation (any rank order: the fold sorts by (infoset, tree)) to
@@ -234,6 +237,12 @@ int64_t rbp_isoset_size(rbp_isoset_t* h);
 int rbp_isoset_export(rbp_isoset_t* h, int64_t offset, int64_t count, uint64_t* pocket_out, uint64_t* public_out, uint8_t* abs_out);
 /* attach the `Lookup` column isomorphism → abstraction index (e.g. `rbp_kmeans_assign` output narrowed to u8) */
 int rbp_isoset_set_abstractions(rbp_isoset_t* h, const uint8_t* abs);
+/* `i64::from(Observation)` and back (crates/deuce/src/observation.rs:130-163; host-side format conversion): board cards then
+ * pocket cards in ascending card order, one byte (1 + card) each, first card in the highest used byte */
+void rbp_obs_encode(const uint64_t* pocket, const uint64_t* public_, int64_t n, int64_t* obs_out);
+void rbp_obs_decode(const int64_t* obs, int64_t n, uint64_t* pocket_out, uint64_t* public_out);
+/* the (obs i64, abs i16) rows the reference stores in its `isomorphism` table (crates/lloyd/src/lookup.rs `Streamable::rows`) */
+int rbp_isoset_export_rows(rbp_isoset_t* h, int64_t offset, int64_t count, int64_t* obs_out, int16_t* abs_out);
 /* `Lookup::grow(Street::Rive)` (crates/lloyd/src/lookup.rs:177-184): column = `Abstraction::from(equity)` of every river iso */
 int rbp_isoset_river_buckets(rbp_isoset_t* h);
 /* `Lookup::projections` (lookup.rs:46-66): for parent observations [offset, offset+count) the histogram over the child

@@ -115,6 +115,12 @@ def load_library():
     l.rbp_nlhe_import.argtypes = [vp, vp, u64, u64]
     l.rbp_nlhe_sample.argtypes = [vp]
     l.rbp_nlhe_set_lookup.argtypes = [vp, vp]
+    l.rbp_nlhe_set_lookup_rows.argtypes = [vp, vp, vp, i64]
+    l.rbp_obs_encode.argtypes = [vp, vp, i64, vp]
+    l.rbp_obs_encode.restype = None
+    l.rbp_obs_decode.argtypes = [vp, i64, vp, vp]
+    l.rbp_obs_decode.restype = None
+    l.rbp_isoset_export_rows.argtypes = [vp, i64, i64, vp, vp]
     l.rbp_nlhe_partition_records.argtypes = [vp, P(vp), P(u64)]
     l.rbp_nlhe_touched_rows.argtypes = [vp, P(vp), P(u64), P(i32)]
     l.rbp_nlhe_apply_rows.argtypes = [vp, vp, u64]

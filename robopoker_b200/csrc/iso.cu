@@ -227,6 +227,43 @@ int rbp_isoset_export(rbp_isoset_t* h, int64_t offset, int64_t count, uint64_t* 
     }
     return RBP_OK;
 }
+// `i64::from(Observation)` / `Observation::from(i64)` (crates/deuce/src/observation.rs:130-163): the cards of the board, then of the
+// pocket, each in ascending card order, one byte per card (1 + card), first card in the highest used byte.
+void rbp_obs_encode(const uint64_t* pocket, const uint64_t* pub, int64_t n, int64_t* obs_out) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t acc = 0;
+        for (uint64_t h : {pub[i], pocket[i]})
+            for (; h; h &= h - 1) acc = acc << 8 | (uint64_t)(1 + __builtin_ctzll(h));
+        obs_out[i] = (int64_t)acc;
+    }
+}
+void rbp_obs_decode(const int64_t* obs, int64_t n, uint64_t* pocket_out, uint64_t* pub_out) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t pocket = 0, pub = 0;
+        int k = 0;
+        for (uint64_t bits = (uint64_t)obs[i]; bits & 0xFF; bits >>= 8, ++k) {
+            const uint64_t card = 1ull << ((bits & 0xFF) - 1);
+            if (k < 2) pocket |= card; else pub |= card;
+        }
+        pocket_out[i] = pocket; pub_out[i] = pub;
+    }
+}
+// rows of the reference's `isomorphism` table (crates/lloyd/src/lookup.rs Streamable rows: obs i64, abs i16)
+int rbp_isoset_export_rows(rbp_isoset_t* h, int64_t offset, int64_t count, int64_t* obs_out, int16_t* abs_out) {
+    if (!h || !obs_out || offset < 0 || count < 0 || offset + count > h->n) return RBP_ERR_INVALID;
+    if (abs_out && !h->have_abs) { set_last_error("isoset has no abstraction column yet"); return RBP_ERR_STATE; }
+    RBP_CUDA(cudaSetDevice(h->device));
+    std::vector<uint64_t> p(count), b(count);
+    std::vector<uint8_t> a(abs_out ? count : 0);
+    RBP_CUDA(cudaMemcpy(p.data(), h->pocket + offset, count * 8, cudaMemcpyDeviceToHost));
+    RBP_CUDA(cudaMemcpy(b.data(), h->pub + offset, count * 8, cudaMemcpyDeviceToHost));
+    rbp_obs_encode(p.data(), b.data(), count, obs_out);
+    if (abs_out) {
+        RBP_CUDA(cudaMemcpy(a.data(), h->abs + offset, count, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < count; ++i) abs_out[i] = (int16_t)(h->street << 8 | a[i]);  // kicker/src/abstraction.rs:15-60
+    }
+    return RBP_OK;
+}
 int rbp_isoset_set_abstractions(rbp_isoset_t* h, const uint8_t* abs) {
     if (!h || !abs) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));

@@ -93,6 +93,13 @@ class IsoSet:
                    "rbp_isoset_export")
         return (p, b, a) if with_abs else (p, b)
 
+    def export_rows(self, offset=0, count=None):
+        """Rows of the reference's `isomorphism` table: (obs i64 = i64::from(Isomorphism), abs i16 = i16::from(Abstraction))."""
+        count = len(self) - offset if count is None else count
+        obs, a = np.zeros(count, np.int64), np.zeros(count, np.int16)
+        _ffi.check(self._lib.rbp_isoset_export_rows(self._h, offset, count, obs.ctypes.data, a.ctypes.data), "rbp_isoset_export_rows")
+        return obs, a
+
     def set_abstractions(self, abs_):
         abs_ = np.ascontiguousarray(abs_, dtype=np.uint8)
         assert len(abs_) == len(self)
@@ -109,3 +116,20 @@ class IsoSet:
         miss = ctypes.c_uint64()
         _ffi.check(self._lib.rbp_isoset_project(self._h, child._h, bins, offset, count, hist.ctypes.data, ctypes.byref(miss)), "rbp_isoset_project")
         return hist, miss.value
+
+
+def obs_encode(pocket, public):
+    """`i64::from(Observation)` (crates/deuce/src/observation.rs:130-141) for card-mask arrays."""
+    pocket = np.ascontiguousarray(pocket, dtype=np.uint64)
+    public = np.ascontiguousarray(public, dtype=np.uint64)
+    out = np.zeros(len(pocket), np.int64)
+    _ffi.lib().rbp_obs_encode(pocket.ctypes.data, public.ctypes.data, len(pocket), out.ctypes.data)
+    return out
+
+
+def obs_decode(obs):
+    """`Observation::from(i64)` (observation.rs:143-163) → (pocket masks, public masks)."""
+    obs = np.ascontiguousarray(obs, dtype=np.int64)
+    p, b = np.zeros(len(obs), np.uint64), np.zeros(len(obs), np.uint64)
+    _ffi.lib().rbp_obs_decode(obs.ctypes.data, len(obs), p.ctypes.data, b.ctypes.data)
+    return p, b

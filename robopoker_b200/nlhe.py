@@ -82,6 +82,13 @@ class Nlhe:
         abstraction column is filled (river equity buckets, or the k-means assignments of that street)."""
         _ffi.check(self._lib.rbp_nlhe_set_lookup(self._h, isoset._h), "rbp_nlhe_set_lookup")
 
+    def set_lookup_rows(self, obs, abs_):
+        """The same from the reference's `isomorphism` table rows (obs i64, abs i16) of ONE street."""
+        obs = np.ascontiguousarray(obs, dtype=np.int64)
+        abs_ = np.ascontiguousarray(abs_, dtype=np.int16)
+        assert len(obs) == len(abs_)
+        _ffi.check(self._lib.rbp_nlhe_set_lookup_rows(self._h, obs.ctypes.data, abs_.ctypes.data, len(obs)), "rbp_nlhe_set_lookup_rows")
+
     # multi-GPU exchange (robopoker_b200.distributed.ShardedNlhe)
     def sample(self):
         _ffi.check(self._lib.rbp_nlhe_sample(self._h), "rbp_nlhe_sample")

@@ -49,3 +49,29 @@ def test_turn_histogram_shape(oracle):
     n, pocket, public = oracle.isomorphisms("turn", cap=64)
     h = oracle.turn_histograms(pocket, public, threads=8)
     assert (h.sum(axis=1) == 46).all()       # 46 river children per turn observation (street.rs:120-126)
+
+
+def test_observation_i64_encoding_roundtrip():
+    """`i64::from(Observation)` / `Observation::from(i64)` (crates/deuce/src/observation.rs:130-163): board cards, then pocket
+    cards, ascending, one byte (1 + card) each, first card highest.  Host-side format conversion of librbp_b200."""
+    from robopoker_b200 import deuce
+
+    def card(s):
+        return "23456789TJQKA".index(s[0]) * 4 + "cdhs".index(s[1])
+
+    pocket = np.array([1 << card("2c") | 1 << card("Ts")], np.uint64)
+    public = np.array([1 << card("Jc") | 1 << card("Js") | 1 << card("3d")], np.uint64)
+    want = 0
+    for c in ("3d", "Jc", "Js", "2c", "Ts"):
+        want = want << 8 | (card(c) + 1)
+    assert int(deuce.obs_encode(pocket, public)[0]) == want
+    rng = np.random.default_rng(5)
+    ps, bs = [], []
+    for _ in range(2000):
+        cards = rng.choice(52, size=2 + int(rng.choice([0, 3, 4, 5])), replace=False)
+        ps.append(sum(1 << int(c) for c in cards[:2]))
+        bs.append(sum(1 << int(c) for c in cards[2:]))
+    ps, bs = np.array(ps, np.uint64), np.array(bs, np.uint64)
+    obs = deuce.obs_encode(ps, bs)
+    p2, b2 = deuce.obs_decode(obs)
+    assert np.array_equal(p2, ps) and np.array_equal(b2, bs) and len(np.unique(obs)) == len(set(zip(ps.tolist(), bs.tolist())))
