@@ -17,6 +17,7 @@
 // Because every f32 operation and its order match the oracle's, results are bit-identical, so the sampled
 // trajectories of GPU and oracle never diverge.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <mutex>
