@@ -9,8 +9,8 @@ timeout 400 python bench.py > $O/bench_${TAG}_n1.json 2> $O/bench_${TAG}.err
 timeout 400 python bench.py --workload nlhe --steps 30 > $O/bench_${TAG}_nlhe_n1.json 2>> $O/bench_${TAG}.err
 timeout 400 python bench.py --workload nlhe --batch 65536 --steps 10 > $O/bench_${TAG}_nlhe64k_n1.json 2>> $O/bench_${TAG}.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_nlhe_launches.csv python tools/nlhe_probe.py 16384 > $O/ncu_launch_${TAG}.log 2>&1
-for k in value expand fold; do
-  skip=3; [ $k = expand ] && skip=154
+for k in value classify expand fold; do
+  skip=3; [ $k = expand ] && skip=154; [ $k = classify ] && skip=154
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:nlhe_${k}_kernel --launch-skip $skip -c 1 -o $O/${TAG}_nlhe_$k -f python tools/nlhe_probe.py 16384 > $O/ncu_${k}_${TAG}.log 2>&1
 done
 cut -c1-300 $O/bench_${TAG}_n1.json $O/bench_${TAG}_nlhe_n1.json $O/bench_${TAG}_nlhe64k_n1.json
