@@ -251,9 +251,15 @@ def main_nlhe(args):
         # dominant kernel: the value kernel.  Algorithmic bytes per launch: every preorder node read once (16 B) and one
         # 72-byte update record written per walker node — the kernel re-reads nodes once per walker ancestor from L1/L2.
         k_s = phases[2] * 1e-3 / args.steps
+        traffic = None
+        try:  # DRAM bytes per launch from the committed `ncu --set full` capture (taken at 16384 trees/epoch)
+            if args.batch == 16384:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["nlhe_value_kernel"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         alg = (16.0 * nodes + 72.0 * records * args.steps) / args.steps
         roofline = {"bound": "hbm", "kernel": "nlhe_value_kernel", "achieved": alg / k_s / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": alg / k_s / 1e9 / peak, "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                    "frac": alg / k_s / 1e9 / peak, "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
                     "kernel_ms": {"tree_build": phases[1] / args.steps, "value": phases[2] / args.steps,
                                   "resolve_sort": phases[3] / args.steps, "fold": phases[4] / args.steps},
                     "note": "divergent tree walks and serial per-infoset chains: latency-bound, reported (not claimed) against the HBM roofline (SURVEY 8d)"}
