@@ -306,14 +306,19 @@ int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* assign_out, float* upper_out, f
 int rbp_measure_fadd_peak(float* tera_adds_per_s);
 /* CUDA-event timing on the library stream: what = 0 full step, 1 N x K assignment sweep */
 int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out);
+/* SINKHORN layers: work counters since creation / the last reset — out3 = {OT solves, Gauss-Seidel sweeps,
+ * exp terms = Σ over solves of nx·ny·(2·sweeps + 1)} (the unit the flop layer's throughput is reported in); out3 nullable */
+int rbp_kmeans_sinkhorn_stats(rbp_kmeans_t* h, uint64_t* out3, int reset);
 
 /* `Metric::emd` / `Sinkhorn::divergence` (crates/lloyd/src/metric.rs:109-115, sinkhorn.rs:166-171) for explicit pairs:
  * out[t] = max(0, OT(A[ia[t]], B[ib[t]]) - OT(A,A)/2 - OT(B,B)/2) over dense u32 histograms a_counts[na][bins],
  * b_counts[nb][bins].  Log-domain Sinkhorn exactly as sinkhorn.rs:77-139 (defaults T=0.025, 128 iterations, tol 5e-4,
  * hyperparams/sinkhorn.rs:17-23), sequential sums in ascending-bucket order.  exp/ln contract (replaces the platform
- * libm of `f32::exp`/`f32::ln`, which no reference test pins): exp_c = 2^k * P5(r), k = rint(x*log2e),
- * r = x - k*ln2 (0.693359375, -2.12194440e-4 split, fma), Cephes coefficients; ln_c = Cephes logf on m in
- * [sqrt(1/2), sqrt 2); both as fixed IEEE operation sequences without contraction. */
+ * libm of `f32::exp`/`f32::ln`, which no reference test pins): exp_c(x) with x clamped to [-87.33654, 88.72283]
+ * (saturating; the softmin clamps at MIN_POSITIVE anyway): t = fma(x, 1.44269504, 1.5*2^23), k = t - 1.5*2^23,
+ * r = fma(k, 2.12194440e-4, fma(k, -0.693359375, x)), P5 = Cephes expf coefficients in Horner form (one fma per
+ * step), y = fma(P5, r*r, r) + 1, result bits = bits(y) + (bits(t) << 23); ln_c = Cephes logf on m in
+ * [sqrt(1/2), sqrt 2), Horner and tail steps as fma.  Fixed IEEE operation sequences: nothing else is contracted. */
 int rbp_sinkhorn_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb, int bins, const int32_t* ia, const int32_t* ib,
                        int64_t n, const float* tri, float temperature, int iterations, float tolerance, float* out);
 

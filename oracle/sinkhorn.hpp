@@ -5,9 +5,10 @@
 // exp / ln.  The reference calls `f32::exp` / `f32::ln` (platform libm) — "parity unpinned" (SURVEY §8c): no test in
 // the reference pins a value beyond 1e-4 properties, and CUDA's expf/logf differ from glibc's in the last ulp, which
 // is enough to flip a near-tie bucket assignment.  As with the RNG, the path is therefore defined on a CONTRACT both
-// sides implement with identical IEEE operations (no contraction): `exp_c` / `ln_c` below (Cephes-style single
-// precision kernels, ≤ 2 ulp from libm).  `Math::Libm` keeps the literal libm restatement so tests can bound the
-// contract's distance from it; the reference's own property tests (self-divergence < 1e-4, symmetry < 1e-3 on the
+// sides implement with identical IEEE operations (explicit fma, nothing else contracted): `exp_c` / `ln_c` below
+// (Cephes-style single precision kernels, ≤ 2 ulp from libm; exp_c saturates instead of under/overflowing).
+// `Math::Libm` keeps the literal libm restatement so tests can bound the contract's distance from it; the
+// reference's own property tests (self-divergence < 1e-4, symmetry < 1e-3 on the
 // synthetic metric of sinkhorn.rs:252-262) are checked under both.
 #pragma once
 #include <cfloat>
@@ -21,26 +22,25 @@ namespace orc {
 inline float f_from_bits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t bits_of(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
-// exp contract: k = rint(x·log2e); r = x − k·ln2 (two-term, fma); degree-5 Cephes polynomial; exact 2^k scaling
+// exp contract: saturating — x clamped to [ln MIN_POSITIVE, ln MAX] (NaN → lower bound); k = rint(x·log2e) through
+// the 1.5·2^23 shifter; r = x − k·ln2 (two-term split); degree-5 Cephes polynomial in Horner form, every step one
+// fma; 2^k applied by adding k to the exponent field.  Identical IEEE operations on both sides (fmaf is exact).
 inline float exp_c(float x) {
-    if (!(x < 88.72283f)) return x != x ? x : INFINITY;
-    if (x < -103.0f) return 0.0f;
-    const float kf = rintf(x * 1.44269504088896341f);
-    int k = (int)kf;
+    x = fminf(fmaxf(x, -87.33654f), 88.72283f);
+    const float t = fmaf(x, 1.44269504f, 12582912.0f);
+    const float kf = t - 12582912.0f;
     float r = fmaf(kf, -0.693359375f, x);
     r = fmaf(kf, 2.12194440e-4f, r);
     float p = 1.9875691500e-4f;
-    p = p * r + 1.3981999507e-3f;
-    p = p * r + 8.3334519073e-3f;
-    p = p * r + 4.1665795894e-2f;
-    p = p * r + 1.6666665459e-1f;
-    p = p * r + 5.0000001201e-1f;
-    float y = p * (r * r) + r + 1.0f;
-    if (k < -125) { y = y * f_from_bits((uint32_t)(127 - 100) << 23); k += 100; }  // two exact power-of-two scalings
-    if (k > 127) { y = y * f_from_bits((uint32_t)(127 + 100) << 23); k -= 100; }
-    return y * f_from_bits((uint32_t)(k + 127) << 23);
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    const float y = fmaf(p, r * r, r) + 1.0f;
+    return f_from_bits(bits_of(y) + (bits_of(t) << 23));
 }
-// ln contract (x > 0, normal): x = m·2^e with m in [sqrt(1/2), sqrt 2); Cephes logf polynomial in (m − 1)
+// ln contract (x > 0): x = m·2^e with m in [sqrt(1/2), sqrt 2); Cephes logf polynomial in (m − 1), Horner steps fma
 inline float ln_c(float x) {
     if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
     if (x == INFINITY) return x;
@@ -53,20 +53,20 @@ inline float ln_c(float x) {
     if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
     const float z = m * m;
     float y = 7.0376836292e-2f;
-    y = y * m + -1.1514610310e-1f;
-    y = y * m + 1.1676998740e-1f;
-    y = y * m + -1.2420140846e-1f;
-    y = y * m + 1.4249322787e-1f;
-    y = y * m + -1.6668057665e-1f;
-    y = y * m + 2.0000714765e-1f;
-    y = y * m + -2.4999993993e-1f;
-    y = y * m + 3.3333331174e-1f;
+    y = fmaf(y, m, -1.1514610310e-1f);
+    y = fmaf(y, m, 1.1676998740e-1f);
+    y = fmaf(y, m, -1.2420140846e-1f);
+    y = fmaf(y, m, 1.4249322787e-1f);
+    y = fmaf(y, m, -1.6668057665e-1f);
+    y = fmaf(y, m, 2.0000714765e-1f);
+    y = fmaf(y, m, -2.4999993993e-1f);
+    y = fmaf(y, m, 3.3333331174e-1f);
     y = y * m * z;
     const float fe = (float)e;
-    y = y + -2.12194440e-4f * fe;
-    y = y + -0.5f * z;
+    y = fmaf(-2.12194440e-4f, fe, y);
+    y = fmaf(-0.5f, z, y);
     float r = m + y;
-    r = r + 0.693359375f * fe;
+    r = fmaf(0.693359375f, fe, r);
     return r;
 }
 

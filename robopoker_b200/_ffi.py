@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librbp_b200.so")
+# RBP_LIB_PATH: another build of the same library (A/B timing of a kernel change); never a fallback
+LIB_PATH = os.environ.get("RBP_LIB_PATH") or os.path.join(_HERE, "librbp_b200.so")
 
 
 class RbpError(RuntimeError):
@@ -90,6 +91,8 @@ def load_library():
     l.rbp_kmeans_metric.argtypes = [vp, vp]
     l.rbp_kmeans_bounds.argtypes = [vp, vp, vp, vp, vp]
     l.rbp_kmeans_timed.argtypes = [vp, i32, i32, f32p]
+    if hasattr(l, "rbp_kmeans_sinkhorn_stats"):
+        l.rbp_kmeans_sinkhorn_stats.argtypes = [vp, vp, i32]
     l.rbp_measure_fadd_peak.argtypes = [f32p]
     l.rbp_kmeans_set_metric.argtypes = [vp, vp, i32]
     l.rbp_sinkhorn_batch.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp, ctypes.c_float, i32, ctypes.c_float, vp]

@@ -35,6 +35,7 @@ int sk_centroids(KmSk*, uint64_t*, uint64_t*);
 int sk_metric(KmSk*, float*);
 int sk_bounds(KmSk*, uint32_t*, float*, float*, uint8_t*);
 int sk_timed(KmSk*, int, int, float*);
+int sk_stats(KmSk*, uint64_t*, int);
 int sk_batch(const uint32_t*, int, const uint32_t*, int, int, const int32_t*, const int32_t*, int64_t, const float*, float, int, float, float*);
 }  // namespace rbp
 using namespace rbp;
@@ -129,6 +130,11 @@ int rbp_kmeans_bounds(rbp_kmeans_t* h, uint32_t* a, float* u, float* l, uint8_t*
 int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms) {
     if (!ms || iters < 1) return RBP_ERR_INVALID;
     return DISPATCH(h, w1_timed(W1(h), what, iters, ms), sk_timed(SK(h), what, iters, ms));
+}
+int rbp_kmeans_sinkhorn_stats(rbp_kmeans_t* h, uint64_t* out3, int reset) {
+    if (!h) return RBP_ERR_INVALID;
+    if (h->kind != RBP_KMEANS_SINKHORN) { set_last_error("only Sinkhorn layers count OT solves"); return RBP_ERR_STATE; }
+    return sk_stats(SK(h), out3, reset);
 }
 int rbp_sinkhorn_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb, int bins, const int32_t* ia, const int32_t* ib,
                        int64_t n, const float* tri, float temperature, int iterations, float tolerance, float* out) {

@@ -10,6 +10,7 @@
 // point at creation and once per centroid per iteration.  Argument order is preserved where the divergence is not
 // symmetric in floating point: `neighbor` calls distance(c, x), `refresh/rebound` distance(x, c) (elkan.rs:68-77,113-123).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "kmeans_common.cuh"
@@ -17,7 +18,7 @@
 
 namespace rbp {
 
-constexpr int kSkWarps = 8;          // warps (OT problems) per block
+constexpr int kSkWarps = 8;          // max warps (OT problems) per block; the launch picks blockDim = 32 x warps
 constexpr int kPtMax = 64;           // max support of a point (flop children: 47, crates/deuce/src/street.rs:120-126)
 
 struct SkDev {
@@ -34,8 +35,8 @@ struct SkDev {
     unsigned long long* acc;     // [K][bins + 1]
     float* c_self;          // [K]
     float* new_self;        // [K]
-    const float* tri;       // ground metric, Pair::merge order
-    const float* reg;       // tri / temperature
+    const float* tri;       // ground metric, dense symmetric [256][256] (sk_dense_tables)
+    const float* reg;       // metric / temperature, same layout
     float* pair;            // [K][K]
     float* mid;             // [K]
     float* drift;           // [K]
@@ -47,9 +48,10 @@ struct SkDev {
     uint32_t* reassigned;   // [1]
     int pending;
     SkParams hp;
+    unsigned long long* stats;  // {solves, sweeps, exp terms}
 };
 
-__device__ __forceinline__ void load_point(const SkDev& d, int64_t i, uint16_t* idx, float* lnd, int* n_out, int lane) {
+__device__ __forceinline__ void load_point(const SkDev& d, int64_t i, uint8_t* idx, float* lnd, int* n_out, int lane) {
     const int n = d.p_n[i];
     const float w = (float)d.p_w[i];
     for (int t = lane; t < n; t += 32) {
@@ -59,7 +61,7 @@ __device__ __forceinline__ void load_point(const SkDev& d, int64_t i, uint16_t* 
     *n_out = n;
     __syncwarp();
 }
-__device__ __forceinline__ void load_centroid(const unsigned long long* __restrict__ counts, int bins, uint16_t* idx, float* lnd, int* n_out, int lane) {
+__device__ __forceinline__ void load_centroid(const unsigned long long* __restrict__ counts, int bins, uint8_t* idx, float* lnd, int* n_out, int lane) {
     const float w = (float)counts[bins];
     *n_out = sk_load_side([&](int b) { return (float)counts[b]; }, w, bins, idx, lnd, lane);
 }
@@ -69,10 +71,10 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_self_points_kernel(SkDev d) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)kSkWarps + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * kSkWarps) {
+    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         load_point(d, i, w.ix, w.lnmu, &w.nx, lane);
         load_point(d, i, w.iy, w.lnnu, &w.ny, lane);
-        const float c = sk_solve(w, d.tri, d.reg, d.hp, lane);
+        const float c = sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats);
         if (lane == 0) d.p_self[i] = c;
         __syncwarp();
     }
@@ -81,11 +83,11 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_self_centroids_kernel(SkDev 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int j = blockIdx.x * kSkWarps + (threadIdx.x >> 5); j < d.k; j += gridDim.x * kSkWarps) {
+    for (int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < d.k; j += gridDim.x * (blockDim.x >> 5)) {
         const unsigned long long* c = counts + (size_t)j * (d.bins + 1);
         load_centroid(c, d.bins, w.ix, w.lnmu, &w.nx, lane);
         load_centroid(c, d.bins, w.iy, w.lnnu, &w.ny, lane);
-        const float v = sk_solve(w, d.tri, d.reg, d.hp, lane);
+        const float v = sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats);
         if (lane == 0) out[j] = v;
         __syncwarp();
     }
@@ -99,13 +101,13 @@ sk_centroid_pairs_kernel(SkDev d, const unsigned long long* __restrict__ A, cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int t = blockIdx.x * kSkWarps + (threadIdx.x >> 5); t < total; t += gridDim.x * kSkWarps) {
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += gridDim.x * (blockDim.x >> 5)) {
         const int i = mode == 0 ? t / d.k : t, j = mode == 0 ? t % d.k : t;
         float v = 0.0f;
         if (!(mode == 0 && i == j)) {  // elkan.rs:91-93 pairwise(i, i) = 0
             load_centroid(A + (size_t)i * (d.bins + 1), d.bins, w.ix, w.lnmu, &w.nx, lane);
             load_centroid(B + (size_t)j * (d.bins + 1), d.bins, w.iy, w.lnnu, &w.ny, lane);
-            v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane), selfA[i], selfB[j]);
+            v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), selfA[i], selfB[j]);
         }
         if (lane == 0) out[t] = v;
         __syncwarp();
@@ -149,12 +151,12 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_pp_update_kernel(SkDev d, fl
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)kSkWarps + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * kSkWarps) {
+    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         if (first) { if (lane == 0) pot[i] = 1.0f; continue; }
         const int64_t pk = *pick;
         load_point(d, pk, w.ix, w.lnmu, &w.nx, lane);
         load_point(d, i, w.iy, w.lnnu, &w.ny, lane);
-        const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane), d.p_self[pk], d.p_self[i]);
+        const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.p_self[pk], d.p_self[i]);
         if (lane == 0) {
             const float d2 = dist * dist;
             float p = pot[i];
@@ -183,13 +185,13 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_assign_kernel(SkDev d, uint3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)kSkWarps + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * kSkWarps) {
+    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         float best = 0.0f;
         int bestj = -1;
         for (int j = 0; j < d.k; ++j) {
             load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.ix, w.lnmu, &w.nx, lane);  // mu = centroid
             load_point(d, i, w.iy, w.lnnu, &w.ny, lane);                                              // nu = point
-            const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane), d.c_self[j], d.p_self[i]);
+            const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.c_self[j], d.p_self[i]);
             if (bestj < 0 || dist < best) { best = dist; bestj = j; }
             __syncwarp();
         }
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_step_kernel(SkDev d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)kSkWarps + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * kSkWarps) {
+    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         uint32_t c = d.assign[i];
         const uint32_t c_prior = c;
         float u = d.upper[i];
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_step_kernel(SkDev d) {
             auto dist_to = [&](int j) {  // distance(x, c_j): mu = point, nu = centroid
                 load_point(d, i, w.ix, w.lnmu, &w.nx, lane);
                 load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.iy, w.lnnu, &w.ny, lane);
-                const float v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane), d.p_self[i], d.c_self[j]);
+                const float v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.p_self[i], d.c_self[j]);
                 __syncwarp();
                 return v;
             };
@@ -279,7 +281,7 @@ sk_batch_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t t = blockIdx.x * (int64_t)kSkWarps + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * kSkWarps) {
+    for (int64_t t = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         const int a = mode == 0 ? (int)t : ia[t], b = mode == 0 ? (int)t : ib[t];
         const uint32_t* ha = A + (size_t)a * bins;
         const uint32_t* hb = (mode == 0 ? A : B) + (size_t)b * bins;
@@ -316,7 +318,7 @@ struct KmSk : rbp_kmeans {
     float* reg_dev = nullptr;
     uint32_t* tmp_assign = nullptr;
     float* tmp_dist = nullptr;
-    int nb = 0, grid = 0;
+    int nb = 0, grid = 0, warps = kSkWarps, threads = kSkWarps * 32;
     size_t smem = 0;
     bool have_metric = false, have_centroids = false, have_bounds = false;
 };
@@ -351,7 +353,7 @@ int supload(KmSk* h, const std::vector<T>& v, const T** out) {
     return RBP_OK;
 }
 int centroid_selfs(KmSk* h, const unsigned long long* counts, float* out) {
-    sk_self_centroids_kernel<<<std::min(h->grid, (h->d.k + kSkWarps - 1) / kSkWarps), kSkWarps * 32, h->smem, h->stream>>>(h->d, counts, out);
+    sk_self_centroids_kernel<<<std::min(h->grid, (h->d.k + h->warps - 1) / h->warps), h->threads, h->smem, h->stream>>>(h->d, counts, out);
     RBP_LAUNCHED();
     return RBP_OK;
 }
@@ -406,13 +408,21 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     if ((st = salloc(h, 1, &h->pick))) return fail(st);
     if ((st = salloc(h, (size_t)k, &h->chosen))) return fail(st);
     if ((st = salloc(h, (size_t)k * (k - 1) / 2 + 1, &h->tri_out))) return fail(st);
-    if ((st = salloc(h, (size_t)bins * (bins - 1) / 2 + 1, &h->tri_dev))) return fail(st);
-    if ((st = salloc(h, (size_t)bins * (bins - 1) / 2 + 1, &h->reg_dev))) return fail(st);
+    if ((st = salloc(h, (size_t)kSkLd * kSkLd, &h->tri_dev))) return fail(st);
+    if ((st = salloc(h, (size_t)kSkLd * kSkLd, &h->reg_dev))) return fail(st);
     if ((st = salloc(h, (size_t)n, &h->tmp_assign))) return fail(st);
     if ((st = salloc(h, (size_t)n, &h->tmp_dist))) return fail(st);
     d.tri = h->tri_dev; d.reg = h->reg_dev;
-    h->smem = kSkWarps * sizeof(SkWarp);
-    h->grid = 148 * 2;
+    if ((st = salloc(h, 3, &d.stats))) return fail(st);
+    // launch shape: 8 warps x 2 blocks per SM by default (11 KB of scratch per warp); RBP_SK_WARPS / RBP_SK_BLOCKS_PER_SM
+    // override it for tuning runs
+    int sms = 148, blocks_per_sm = 2;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("RBP_SK_WARPS")) h->warps = std::max(1, std::min(kSkWarps, atoi(e)));
+    if (const char* e = getenv("RBP_SK_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, std::min(16, atoi(e)));
+    h->threads = h->warps * 32;
+    h->smem = h->warps * sizeof(SkWarp);
+    h->grid = sms * blocks_per_sm;
     const void* kernels[] = {(const void*)sk_self_points_kernel, (const void*)sk_self_centroids_kernel, (const void*)sk_centroid_pairs_kernel,
                              (const void*)sk_pp_update_kernel, (const void*)sk_assign_kernel<true>, (const void*)sk_assign_kernel<false>,
                              (const void*)sk_step_kernel, (const void*)sk_batch_kernel};
@@ -426,12 +436,11 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
 int sk_set_metric(KmSk* h, const float* tri, int bins) {
     if (!h || !tri || bins != h->d.bins) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
-    const size_t T = (size_t)bins * (bins - 1) / 2;
-    std::vector<float> reg(T);
-    for (size_t t = 0; t < T; ++t) reg[t] = tri[t] / h->d.hp.temperature;  // sinkhorn.rs:127-129 regularization
-    RBP_CUDA(cudaMemcpyAsync(h->tri_dev, tri, T * 4, cudaMemcpyHostToDevice, h->stream));
-    RBP_CUDA(cudaMemcpyAsync(h->reg_dev, reg.data(), T * 4, cudaMemcpyHostToDevice, h->stream));
-    sk_self_points_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(h->d);
+    std::vector<float> metric((size_t)kSkLd * kSkLd), reg((size_t)kSkLd * kSkLd);
+    sk_dense_tables(tri, bins, h->d.hp.temperature, metric.data(), reg.data());
+    RBP_CUDA(cudaMemcpyAsync(h->tri_dev, metric.data(), metric.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    RBP_CUDA(cudaMemcpyAsync(h->reg_dev, reg.data(), reg.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    sk_self_points_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(h->d);
     RBP_LAUNCHED();
     RBP_CUDA(cudaStreamSynchronize(h->stream));
     h->have_metric = true;
@@ -442,7 +451,7 @@ int sk_init_pp(KmSk* h, uint64_t seed, int32_t* chosen_out) {
     if (!h->have_metric) { set_last_error("set the ground metric first"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(h->device));
     for (int r = 0; r < h->d.k; ++r) {
-        sk_pp_update_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(h->d, h->pot, h->pick, r == 0);
+        sk_pp_update_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->pot, h->pick, r == 0);
         RBP_LAUNCHED();
         pp_blocksum_kernel<<<h->nb, 128, 0, h->stream>>>(h->pot, h->d.n, h->bsum);
         RBP_LAUNCHED();
@@ -481,7 +490,7 @@ int sk_set_centroids(KmSk* h, const uint64_t* counts) {
 int sk_init_bounds(KmSk* h) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
-    sk_assign_kernel<true><<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(h->d, nullptr, nullptr);
+    sk_assign_kernel<true><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
     RBP_LAUNCHED();
     h->d.pending = 0;
     RBP_CUDA(cudaStreamSynchronize(h->stream));
@@ -493,14 +502,14 @@ int sk_step_local(KmSk* h) {
     if (!h->have_bounds) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
     SkDev& d = h->d;
-    sk_centroid_pairs_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
     RBP_LAUNCHED();
     sk_mid_kernel<<<(d.k + 127) / 128, 128, 0, h->stream>>>(d.pair, d.k, d.mid);
     RBP_LAUNCHED();
     RBP_CUDA(cudaMemsetAsync(d.reassigned, 0, 4, h->stream));
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * 4, h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (d.bins + 1) * 8, h->stream));
-    sk_step_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(d);
+    sk_step_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d);
     RBP_LAUNCHED();
     sk_accumulate_kernel<<<148 * 4, 256, 0, h->stream>>>(d);
     RBP_LAUNCHED();
@@ -513,7 +522,7 @@ int sk_step_finish(KmSk* h, float* drift_out, uint32_t* sizes_out, uint32_t* rea
     int st = centroid_selfs(h, d.acc, d.new_self);
     if (st) return st;
     // drift_j = distance(new_j, old_j)  (elkan.rs:107-109)
-    sk_centroid_pairs_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(d, d.acc, d.new_self, d.ccount, d.c_self, 1, d.k, d.drift);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.acc, d.new_self, d.ccount, d.c_self, 1, d.k, d.drift);
     RBP_LAUNCHED();
     std::swap(d.acc, d.ccount);
     std::swap(d.new_self, d.c_self);
@@ -528,7 +537,7 @@ int sk_step_finish(KmSk* h, float* drift_out, uint32_t* sizes_out, uint32_t* rea
 int sk_assign(KmSk* h, uint32_t* assign_out, float* dist_out) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
-    sk_assign_kernel<false><<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+    sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
     RBP_LAUNCHED();
     RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (dist_out) RBP_CUDA(cudaMemcpyAsync(dist_out, h->tmp_dist, h->d.n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -554,7 +563,7 @@ int sk_metric(KmSk* h, float* tri_out) {
     SkDev& d = h->d;
     const int total = d.k * (d.k - 1) / 2;
     if (total == 0) return RBP_OK;
-    sk_centroid_pairs_kernel<<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
     RBP_LAUNCHED();
     sk_metric_kernel<<<1, 256, 0, h->stream>>>(d.pair, d.k, h->tri_out);
     RBP_LAUNCHED();
@@ -590,6 +599,13 @@ int sk_counters(KmSk* h, void** dev_sizes, void** dev_reassigned) {
     return RBP_OK;
 }
 void* sk_stream(KmSk* h) { return (void*)h->stream; }
+int sk_stats(KmSk* h, uint64_t* out, int reset) {
+    RBP_CUDA(cudaSetDevice(h->device));
+    if (out) RBP_CUDA(cudaMemcpyAsync(out, h->d.stats, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) RBP_CUDA(cudaMemsetAsync(h->d.stats, 0, 3 * sizeof(uint64_t), h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return RBP_OK;
+}
 
 int sk_timed(KmSk* h, int what, int iters, float* ms_out) {
     RBP_CUDA(cudaSetDevice(h->device));
@@ -601,7 +617,7 @@ int sk_timed(KmSk* h, int what, int iters, float* ms_out) {
         int st;
         if (what == 0) { st = sk_step_local(h); if (!st) st = sk_step_finish(h, nullptr, nullptr, nullptr); }
         else {
-            sk_assign_kernel<false><<<h->grid, kSkWarps * 32, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+            sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
             g_launches.fetch_add(1);
             st = cudaGetLastError() == cudaSuccess ? RBP_OK : RBP_ERR_CUDA;
         }
@@ -622,21 +638,21 @@ int sk_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb,
         return RBP_ERR_INVALID;
     if (rbp_device_count() < 1) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
     if (n == 0) return RBP_OK;
-    const size_t T = (size_t)bins * (bins - 1) / 2;
-    std::vector<float> reg(T);
-    for (size_t t = 0; t < T; ++t) reg[t] = tri[t] / temperature;
+    const size_t T = (size_t)kSkLd * kSkLd;
+    std::vector<float> metric(T), reg(T);
+    sk_dense_tables(tri, bins, temperature, metric.data(), reg.data());
     uint32_t *dA = nullptr, *dB = nullptr;
     int32_t *dia = nullptr, *dib = nullptr;
     float *dtri = nullptr, *dreg = nullptr, *dsa = nullptr, *dsb = nullptr, *dout = nullptr;
     RBP_CUDA(cudaMalloc(&dA, (size_t)na * bins * 4)); RBP_CUDA(cudaMalloc(&dB, (size_t)nb * bins * 4));
     RBP_CUDA(cudaMalloc(&dia, n * 4)); RBP_CUDA(cudaMalloc(&dib, n * 4));
-    RBP_CUDA(cudaMalloc(&dtri, (T + 1) * 4)); RBP_CUDA(cudaMalloc(&dreg, (T + 1) * 4));
+    RBP_CUDA(cudaMalloc(&dtri, T * 4)); RBP_CUDA(cudaMalloc(&dreg, T * 4));
     RBP_CUDA(cudaMalloc(&dsa, na * 4)); RBP_CUDA(cudaMalloc(&dsb, nb * 4)); RBP_CUDA(cudaMalloc(&dout, n * 4));
     RBP_CUDA(cudaMemcpy(dA, a_counts, (size_t)na * bins * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dB, b_counts, (size_t)nb * bins * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dia, ia, n * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dib, ib, n * 4, cudaMemcpyHostToDevice));
-    RBP_CUDA(cudaMemcpy(dtri, tri, T * 4, cudaMemcpyHostToDevice));
+    RBP_CUDA(cudaMemcpy(dtri, metric.data(), T * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dreg, reg.data(), T * 4, cudaMemcpyHostToDevice));
     const size_t smem = kSkWarps * sizeof(SkWarp);
     RBP_CUDA(cudaFuncSetAttribute(sk_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

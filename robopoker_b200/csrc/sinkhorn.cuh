@@ -2,34 +2,43 @@
 //
 // One warp solves one (mu, nu) problem.  The reference's arithmetic is reproduced operation for operation: log-domain
 // Gauss-Seidel sweeps, every Σ sequential in ascending-bucket order, MIN_POSITIVE clamps, the L1 stopping rule on
-// exp(potential), the single-accumulator row-major cost.  Parallelism comes only from independent rows: a lane owns
-// one x (resp. one y) and runs its softmin sum sequentially; the order-sensitive scalar sums (`delta`, `cost`) are
-// fed lane by lane through shuffles.  exp/ln follow the contract of include/rbp.h (`exp_c` / `ln_c`: fixed IEEE
-// operation sequences, no contraction — this file is compiled -fmad=false), so results are bit-identical to the oracle.
+// exp(potential), the single-accumulator row-major cost.  Only the ADDITIONS of a softmin are order-sensitive; its
+// exp terms are independent, so a half-sweep picks, per problem shape, the cheaper of two bit-identical schedules:
+//   rows:       a lane owns a target and runs its sum over the sources in a register (full lanes when the target
+//               side is wide — centroids);
+//   transposed: lanes span 32 SOURCES, the exp terms of one 32-source slab go through a [target][source] shared
+//               tile, and lane t then adds row t left to right (narrow target side — a point's ~11 buckets — where
+//               `rows` would leave two thirds of the warp idle in front of the 256-term loop).
+// The ground metric is a dense symmetric [256][256] table (L1/L2 resident): the broadcast index picks the row, the
+// lane's index the column, so every load is one coalesced line.  exp/ln follow the contract of include/rbp.h
+// (`exp_c` / `ln_c`: fixed IEEE operation sequences with explicit fma — this file is compiled -fmad=false so nothing
+// else contracts), so results are bit-identical to the oracle.
 #pragma once
 #include "common.cuh"
 
 namespace rbp {
 
 constexpr int kSkMaxSupport = 256;  // KMEANS_MAX_CLUSTER_COUNT (crates/pokerkit/src/lib.rs:185)
+constexpr int kSkLd = 256;          // row stride of the dense ground-metric tables
+constexpr int kSkTile = 36;         // row stride of the transposed tile (16-byte rows, conflict-free LDS.128)
 
+// exp contract (include/rbp.h): saturating, x clamped to [ln MIN_POSITIVE, ln MAX]; k = rint(x·log2e) through the
+// 1.5·2^23 shifter; r = x − k·ln2 (two-term split); degree-5 Cephes polynomial in Horner form, all fma; 2^k applied
+// by adding k to the exponent field.
 __device__ __forceinline__ float exp_c(float x) {
-    if (!(x < 88.72283f)) return x != x ? x : INFINITY;
-    if (x < -103.0f) return 0.0f;
-    const float kf = rintf(x * 1.44269504088896341f);
-    int k = (int)kf;
+    x = fminf(fmaxf(x, -87.33654f), 88.72283f);
+    const float t = __fmaf_rn(x, 1.44269504f, 12582912.0f);
+    const float kf = t - 12582912.0f;
     float r = __fmaf_rn(kf, -0.693359375f, x);
     r = __fmaf_rn(kf, 2.12194440e-4f, r);
     float p = 1.9875691500e-4f;
-    p = p * r + 1.3981999507e-3f;
-    p = p * r + 8.3334519073e-3f;
-    p = p * r + 4.1665795894e-2f;
-    p = p * r + 1.6666665459e-1f;
-    p = p * r + 5.0000001201e-1f;
-    float y = p * (r * r) + r + 1.0f;
-    if (k < -125) { y = y * __uint_as_float((uint32_t)(127 - 100) << 23); k += 100; }
-    if (k > 127) { y = y * __uint_as_float((uint32_t)(127 + 100) << 23); k -= 100; }
-    return y * __uint_as_float((uint32_t)(k + 127) << 23);
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float y = __fmaf_rn(p, r * r, r) + 1.0f;
+    return __uint_as_float(__float_as_uint(y) + (__float_as_uint(t) << 23));
 }
 __device__ __forceinline__ float ln_c(float x) {
     if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
@@ -41,20 +50,20 @@ __device__ __forceinline__ float ln_c(float x) {
     if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
     const float z = m * m;
     float y = 7.0376836292e-2f;
-    y = y * m + -1.1514610310e-1f;
-    y = y * m + 1.1676998740e-1f;
-    y = y * m + -1.2420140846e-1f;
-    y = y * m + 1.4249322787e-1f;
-    y = y * m + -1.6668057665e-1f;
-    y = y * m + 2.0000714765e-1f;
-    y = y * m + -2.4999993993e-1f;
-    y = y * m + 3.3333331174e-1f;
+    y = __fmaf_rn(y, m, -1.1514610310e-1f);
+    y = __fmaf_rn(y, m, 1.1676998740e-1f);
+    y = __fmaf_rn(y, m, -1.2420140846e-1f);
+    y = __fmaf_rn(y, m, 1.4249322787e-1f);
+    y = __fmaf_rn(y, m, -1.6668057665e-1f);
+    y = __fmaf_rn(y, m, 2.0000714765e-1f);
+    y = __fmaf_rn(y, m, -2.4999993993e-1f);
+    y = __fmaf_rn(y, m, 3.3333331174e-1f);
     y = y * m * z;
     const float fe = (float)e;
-    y = y + -2.12194440e-4f * fe;
-    y = y + -0.5f * z;
+    y = __fmaf_rn(-2.12194440e-4f, fe, y);
+    y = __fmaf_rn(-0.5f, z, y);
     float r = m + y;
-    r = r + 0.693359375f * fe;
+    r = __fmaf_rn(0.693359375f, fe, r);
     return r;
 }
 
@@ -65,24 +74,31 @@ struct SkParams {
 };
 
 // per-warp scratch in shared memory
-struct SkWarp {
-    float lhs[kSkMaxSupport], rhs[kSkMaxSupport], nxt[kSkMaxSupport];
+struct __align__(16) SkWarp {
+    float lhs[kSkMaxSupport], rhs[kSkMaxSupport];    // potentials
+    float elhs[kSkMaxSupport], erhs[kSkMaxSupport];  // exp_c(potential): delta()'s `prev` term is last sweep's `next`
     float lnmu[kSkMaxSupport], lnnu[kSkMaxSupport];
-    uint16_t ix[kSkMaxSupport], iy[kSkMaxSupport];
+    float tile[32 * kSkTile];
+    uint8_t ix[kSkMaxSupport], iy[kSkMaxSupport];    // ascending support (bucket ids < 256)
     int nx, ny;
 };
 
-// ground metric: `tri` in Pair::merge order; `reg` = tri / temperature precomputed element-wise (same f32 quotient
-// the reference forms on every access, sinkhorn.rs:127-129)
-__device__ __forceinline__ float tri_at(const float* __restrict__ t, int x, int y) {
-    if (x == y) return 0.0f;
-    const int lo = x < y ? x : y, hi = x < y ? y : x;
-    return __ldg(t + (size_t)hi * (hi - 1) / 2 + lo);
+// Dense symmetric ground-metric tables from `tri` in Pair::merge order (pair.rs:36-39): metric[x][y] = raw_distance
+// (0 on the diagonal, metric.rs:42-54); reg = metric / temperature element-wise — the same f32 quotient the reference
+// forms on every access (sinkhorn.rs:127-129).  Host side.
+inline void sk_dense_tables(const float* tri, int bins, float temperature, float* metric, float* reg) {
+    for (size_t i = 0; i < (size_t)kSkLd * kSkLd; ++i) { metric[i] = 0.0f; reg[i] = 0.0f; }
+    for (int hi = 1; hi < bins; ++hi)
+        for (int lo = 0; lo < hi; ++lo) {
+            const float c = tri[(size_t)hi * (hi - 1) / 2 + lo], q = c / temperature;
+            metric[(size_t)hi * kSkLd + lo] = c; metric[(size_t)lo * kSkLd + hi] = c;
+            reg[(size_t)hi * kSkLd + lo] = q; reg[(size_t)lo * kSkLd + hi] = q;
+        }
 }
 
 // Load a dense histogram (count accessor) into a sparse side of the warp scratch: ascending support, ln(density).
 template <class CountAt>
-__device__ __forceinline__ int sk_load_side(CountAt cnt, float weight, int bins, uint16_t* idx, float* lnd, int lane) {
+__device__ __forceinline__ int sk_load_side(CountAt cnt, float weight, int bins, uint8_t* idx, float* lnd, int lane) {
     int n = 0;
     for (int b0 = 0; b0 < bins; b0 += 32) {
         const int b = b0 + lane;
@@ -90,7 +106,7 @@ __device__ __forceinline__ int sk_load_side(CountAt cnt, float weight, int bins,
         const unsigned m = __ballot_sync(0xFFFFFFFFu, c > 0.0f);
         if (c > 0.0f) {
             const int pos = n + __popc(m & ((1u << lane) - 1u));
-            idx[pos] = (uint16_t)b;
+            idx[pos] = (uint8_t)b;
             lnd[pos] = ln_c(c / weight);  // bins.rs:58-60 density, then `.ln()` (sinkhorn.rs:113)
         }
         n += __popc(m);
@@ -99,79 +115,153 @@ __device__ __forceinline__ int sk_load_side(CountAt cnt, float weight, int bins,
     return n;
 }
 
-// ordered sum of one value per lane (lanes 0..m-1), continuing `acc`
-__device__ __forceinline__ float ordered_add(float acc, float v, int m) {
-    for (int k = 0; k < m; ++k) acc = acc + __shfl_sync(0xFFFFFFFFu, v, k);
+// acc + v(lane 0) + v(lane 1) + … + v(lane 31), left to right, on every lane.  Lanes outside the support pass +0.0,
+// which is an exact no-op on a sum that starts at +0.0.  `buf`: 32 floats of warp scratch, 16-byte aligned.
+__device__ __forceinline__ float ordered_sum32(float acc, float v, float* buf, int lane) {
+    buf[lane] = v;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 w = reinterpret_cast<const float4*>(buf)[q];
+        acc = acc + w.x; acc = acc + w.y; acc = acc + w.z; acc = acc + w.w;
+    }
+    __syncwarp();
     return acc;
 }
 
-// OT cost of the problem currently loaded in `w` (both sides filled by sk_load_side)
-__device__ __forceinline__ float sk_solve(SkWarp& w, const float* __restrict__ tri, const float* __restrict__ reg, const SkParams hp, int lane) {
+// One Gauss-Seidel half-sweep (sinkhorn.rs:96-129 `lhs()` / `rhs()` + `delta`): for every target t
+//   next_t = ln dens_t − ln Σ_s max(exp(pot_s − reg[t][s]), MIN_POSITIVE)      (Σ sequential over the source support)
+// replaces pot_t and returns Σ_t |exp(next_t) − exp(prev_t)| (sequential over the target support).
+__device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, float* __restrict__ e_t, const float* __restrict__ lnd_t,
+                                               const uint8_t* __restrict__ idx_t, int n_t, const float* __restrict__ pot_s,
+                                               const uint8_t* __restrict__ idx_s, int n_s, float* __restrict__ tile,
+                                               const float* __restrict__ reg, int lane) {
+    float err = 0.0f;
+    // issue-slot model: rows = ceil(n_t/32)·n_s exp steps; transposed = n_t·ceil(n_s/32) exp steps + the row adds
+    const int cost_rows = ((n_t + 31) >> 5) * n_s;
+    const int cost_tr = n_t * ((n_s + 31) >> 5) + (n_s >> 4) + 1;
+    if (n_t <= 32 && cost_tr < cost_rows) {
+        float s = 0.0f;  // lane t: running sum of target t
+        const int n_t4 = (n_t + 3) & ~3;  // rows n_t..n_t4-1 of the tile are written (stale bucket ids, valid table rows) and never read
+        for (int s0 = 0; s0 < n_s; s0 += 32) {
+            const int si = s0 + lane;
+            const bool live = si < n_s;
+            const float ps = live ? pot_s[si] : 0.0f;
+            const float* __restrict__ col = reg + (live ? (int)idx_s[si] : 0);
+            uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t);
+            float c0 = __ldg(col + (int)r4.x * kSkLd), c1 = __ldg(col + (int)r4.y * kSkLd);
+            float c2 = __ldg(col + (int)r4.z * kSkLd), c3 = __ldg(col + (int)r4.w * kSkLd);
+            for (int t = 0; t < n_t4; t += 4) {
+                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                if (t + 4 < n_t4) {  // next group's table loads run under this group's arithmetic
+                    r4 = *reinterpret_cast<const uchar4*>(idx_t + t + 4);
+                    m0 = __ldg(col + (int)r4.x * kSkLd); m1 = __ldg(col + (int)r4.y * kSkLd);
+                    m2 = __ldg(col + (int)r4.z * kSkLd); m3 = __ldg(col + (int)r4.w * kSkLd);
+                }
+                const float e0 = fmaxf(exp_c(ps - c0), kEps), e1 = fmaxf(exp_c(ps - c1), kEps);
+                const float e2 = fmaxf(exp_c(ps - c2), kEps), e3 = fmaxf(exp_c(ps - c3), kEps);
+                tile[(t + 0) * kSkTile + lane] = live ? e0 : 0.0f;
+                tile[(t + 1) * kSkTile + lane] = live ? e1 : 0.0f;
+                tile[(t + 2) * kSkTile + lane] = live ? e2 : 0.0f;
+                tile[(t + 3) * kSkTile + lane] = live ? e3 : 0.0f;
+                c0 = m0; c1 = m1; c2 = m2; c3 = m3;
+            }
+            __syncwarp();
+            if (lane < n_t) {
+                const float4* __restrict__ row = reinterpret_cast<const float4*>(tile + lane * kSkTile);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 w = row[q];
+                    s = s + w.x; s = s + w.y; s = s + w.z; s = s + w.w;
+                }
+            }
+            __syncwarp();
+        }
+        float v = 0.0f;
+        if (lane < n_t) {
+            const float nv = lnd_t[lane] - ln_c(s);
+            const float en = exp_c(nv);
+            v = fabsf(en - e_t[lane]);
+            e_t[lane] = en;
+            pot_t[lane] = nv;
+        }
+        err = ordered_sum32(err, v, tile, lane);
+    } else {
+        const int n_s4 = n_s & ~3;
+        for (int t0 = 0; t0 < n_t; t0 += 32) {
+            const int t = t0 + lane;
+            const bool live = t < n_t;
+            const float* __restrict__ col = reg + (live ? (int)idx_t[t] : 0);
+            float s = 0.0f;
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+            if (n_s4) {
+                const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_s);
+                c0 = __ldg(col + (int)r4.x * kSkLd); c1 = __ldg(col + (int)r4.y * kSkLd);
+                c2 = __ldg(col + (int)r4.z * kSkLd); c3 = __ldg(col + (int)r4.w * kSkLd);
+            }
+            for (int q = 0; q < n_s4; q += 4) {
+                const float4 p4 = *reinterpret_cast<const float4*>(pot_s + q);
+                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                if (q + 4 < n_s4) {  // next group's table loads run under this group's arithmetic
+                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_s + q + 4);
+                    m0 = __ldg(col + (int)r4.x * kSkLd); m1 = __ldg(col + (int)r4.y * kSkLd);
+                    m2 = __ldg(col + (int)r4.z * kSkLd); m3 = __ldg(col + (int)r4.w * kSkLd);
+                }
+                const float e0 = fmaxf(exp_c(p4.x - c0), kEps), e1 = fmaxf(exp_c(p4.y - c1), kEps);
+                const float e2 = fmaxf(exp_c(p4.z - c2), kEps), e3 = fmaxf(exp_c(p4.w - c3), kEps);
+                s = s + e0; s = s + e1; s = s + e2; s = s + e3;
+                c0 = m0; c1 = m1; c2 = m2; c3 = m3;
+            }
+            for (int q = n_s4; q < n_s; ++q) s = s + fmaxf(exp_c(pot_s[q] - __ldg(col + (int)idx_s[q] * kSkLd)), kEps);
+            float v = 0.0f;
+            if (live) {
+                const float nv = lnd_t[t] - ln_c(s);
+                const float en = exp_c(nv);
+                v = fabsf(en - e_t[t]);
+                e_t[t] = en;
+                pot_t[t] = nv;
+            }
+            err = ordered_sum32(err, v, tile, lane);
+        }
+    }
+    return err;
+}
+
+// OT cost of the problem currently loaded in `w` (both sides filled by sk_load_side); `metric` / `reg` are the dense
+// tables of sk_dense_tables.  `stats` (nullable): {solves, sweeps, exp terms} counters for the throughput reports.
+__device__ __forceinline__ float sk_solve(SkWarp& w, const float* __restrict__ metric, const float* __restrict__ reg, const SkParams hp, int lane,
+                                          unsigned long long* __restrict__ stats = nullptr) {
     const int nx = w.nx, ny = w.ny;
     const float lx0 = ln_c(1.0f / (float)nx), ly0 = ln_c(1.0f / (float)ny);  // Phi::uniform (phi.rs:25-30)
-    for (int i = lane; i < nx; i += 32) w.lhs[i] = lx0;
-    for (int j = lane; j < ny; j += 32) w.rhs[j] = ly0;
+    const float ex0 = exp_c(lx0), ey0 = exp_c(ly0);
+    for (int i = lane; i < nx; i += 32) { w.lhs[i] = lx0; w.elhs[i] = ex0; }
+    for (int j = lane; j < ny; j += 32) { w.rhs[j] = ly0; w.erhs[j] = ey0; }
     __syncwarp();
+    int sweeps = 0;
     for (int t = 0; t < hp.iterations; ++t) {
-        // lhs(): softmin over y for every x
-        for (int i0 = 0; i0 < nx; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < nx) {
-                const int xi = w.ix[i];
-                float s = 0.0f;
-                for (int j = 0; j < ny; ++j) {
-                    const float e = exp_c(w.rhs[j] - tri_at(reg, xi, w.iy[j]));
-                    s = s + (e > kEps ? e : kEps);
-                }
-                w.nxt[i] = w.lnmu[i] - ln_c(s);
-            }
-        }
-        __syncwarp();
-        float lerr = 0.0f;  // delta(prev, next) — sequential over the support
-        for (int i0 = 0; i0 < nx; i0 += 32) {
-            const int i = i0 + lane;
-            const float v = i < nx ? fabsf(exp_c(w.nxt[i]) - exp_c(w.lhs[i])) : 0.0f;
-            lerr = ordered_add(lerr, v, min(32, nx - i0));
-        }
-        for (int i = lane; i < nx; i += 32) w.lhs[i] = w.nxt[i];
-        __syncwarp();
-        // rhs(): softmin over x for every y, against the NEW lhs
-        for (int j0 = 0; j0 < ny; j0 += 32) {
-            const int j = j0 + lane;
-            if (j < ny) {
-                const int yj = w.iy[j];
-                float s = 0.0f;
-                for (int i = 0; i < nx; ++i) {
-                    const float e = exp_c(w.lhs[i] - tri_at(reg, w.ix[i], yj));
-                    s = s + (e > kEps ? e : kEps);
-                }
-                w.nxt[j] = w.lnnu[j] - ln_c(s);
-            }
-        }
-        __syncwarp();
-        float rerr = 0.0f;
-        for (int j0 = 0; j0 < ny; j0 += 32) {
-            const int j = j0 + lane;
-            const float v = j < ny ? fabsf(exp_c(w.nxt[j]) - exp_c(w.rhs[j])) : 0.0f;
-            rerr = ordered_add(rerr, v, min(32, ny - j0));
-        }
-        for (int j = lane; j < ny; j += 32) w.rhs[j] = w.nxt[j];
-        __syncwarp();
+        const float lerr = sk_half_sweep(w.lhs, w.elhs, w.lnmu, w.ix, nx, w.rhs, w.iy, ny, w.tile, reg, lane);
+        const float rerr = sk_half_sweep(w.rhs, w.erhs, w.lnnu, w.iy, ny, w.lhs, w.ix, nx, w.tile, reg, lane);  // against the NEW lhs
+        ++sweeps;
         if (lerr + rerr < hp.tolerance) break;
+    }
+    if (stats && lane == 0) {
+        atomicAdd(stats + 0, 1ull);
+        atomicAdd(stats + 1, (unsigned long long)sweeps);
+        atomicAdd(stats + 2, (unsigned long long)nx * ny * (2ull * sweeps + 1ull));
     }
     // Coupling::cost: Σ_x Σ_y exp(lhs_x + rhs_y − reg)·C_xy, one accumulator, row-major
     float cost = 0.0f;
     for (int i = 0; i < nx; ++i) {
-        const int xi = w.ix[i];
+        const int row = (int)w.ix[i] * kSkLd;
         const float li = w.lhs[i];
         for (int j0 = 0; j0 < ny; j0 += 32) {
             const int j = j0 + lane;
             float v = 0.0f;
             if (j < ny) {
-                const int yj = w.iy[j];
-                v = exp_c(li + w.rhs[j] - tri_at(reg, xi, yj)) * tri_at(tri, xi, yj);
+                const int at = row + (int)w.iy[j];
+                v = exp_c(li + w.rhs[j] - __ldg(reg + at)) * __ldg(metric + at);
             }
-            cost = ordered_add(cost, v, min(32, ny - j0));
+            cost = ordered_sum32(cost, v, w.tile, lane);
         }
     }
     return cost;

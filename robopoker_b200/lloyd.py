@@ -118,6 +118,14 @@ class Layer:
         _ffi.check(self._lib.rbp_kmeans_timed(self._h, what, iters, ctypes.byref(ms)), "rbp_kmeans_timed")
         return ms.value
 
+    def sinkhorn_stats(self, reset=False):
+        """Work counters of a Sinkhorn layer: (OT solves, Gauss-Seidel sweeps, exp terms) since creation / the last reset."""
+        out = np.zeros(3, np.uint64)
+        if not hasattr(self._lib, "rbp_kmeans_sinkhorn_stats"):  # an older build loaded through RBP_LIB_PATH
+            return 0, 0, 0
+        _ffi.check(self._lib.rbp_kmeans_sinkhorn_stats(self._h, out.ctypes.data, int(reset)), "rbp_kmeans_sinkhorn_stats")
+        return int(out[0]), int(out[1]), int(out[2])
+
     def cluster(self, iterations=32, seed=0):
         """`Layer::cluster` minus persistence: init → bounds → `iterations` Elkan steps → (lookup, metric, future)."""
         self.init_centroids(seed)

@@ -23,10 +23,17 @@ def hist(entries, bins=32):
 
 
 def test_exp_ln_contract_close_to_libm(oracle):
-    xs = np.concatenate([np.linspace(-87, 88, 4001), np.linspace(-1, 1, 2001), [-100.0, -103.5, 0.0]]).astype(np.float32)
+    xs = np.concatenate([np.linspace(-87, 88, 4001), np.linspace(-1, 1, 2001), [-87.33654, 88.72283, 0.0]]).astype(np.float32)
     for x in xs:
         got, ref = oracle.exp_c(float(x)), math.exp(float(x))
         assert abs(got - ref) <= 3e-7 * ref + 3e-45, (x, got, ref)
+    # saturating outside [ln MIN_POSITIVE, ln MAX]: the softmin clamps at MIN_POSITIVE anyway (sinkhorn.rs:120)
+    lo, hi = oracle.exp_c(-87.33654), oracle.exp_c(88.72283)
+    assert 0.0 < lo <= 1.1755e-38 and math.isfinite(hi) and hi > 3.4e38
+    for x in (-100.0, -103.5, -1e30, float("-inf"), float("nan")):
+        assert oracle.exp_c(x) == lo
+    for x in (89.0, 1e30, float("inf")):
+        assert oracle.exp_c(x) == hi
     ys = np.concatenate([np.logspace(-37, 37, 3001), np.linspace(0.5, 2.0, 2001), [1.17549435e-38, 1e-40]]).astype(np.float32)
     for y in ys:
         got, ref = oracle.ln_c(float(y)), math.log(float(y))
