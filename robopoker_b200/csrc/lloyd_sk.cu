@@ -49,8 +49,16 @@ struct SkDev {
     int pending;
     SkParams hp;
     unsigned long long* stats;  // {solves, sweeps, exp terms}
+    unsigned long long* queue;  // next unclaimed point of the running sweep (zeroed before each launch)
 };
 
+// points are claimed one at a time from a device counter: per-point work varies by orders of magnitude once Elkan
+// prunes, and a point costs K full OT solves in the naive sweeps
+__device__ __forceinline__ int64_t next_point(const SkDev& d, int lane) {
+    unsigned long long i = 0;
+    if (lane == 0) i = atomicAdd(d.queue, 1ull);
+    return (int64_t)__shfl_sync(0xFFFFFFFFu, i, 0);
+}
 __device__ __forceinline__ void load_point(const SkDev& d, int64_t i, uint8_t* idx, float* lnd, int* n_out, int lane) {
     const int n = d.p_n[i];
     const float w = (float)d.p_w[i];
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_assign_kernel(SkDev d, uint3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    for (int64_t i = next_point(d, lane); i < d.n; i = next_point(d, lane)) {
         float best = 0.0f;
         int bestj = -1;
         for (int j = 0; j < d.k; ++j) {
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_step_kernel(SkDev d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    for (int64_t i = next_point(d, lane); i < d.n; i = next_point(d, lane)) {
         uint32_t c = d.assign[i];
         const uint32_t c_prior = c;
         float u = d.upper[i];
@@ -414,9 +422,10 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     if ((st = salloc(h, (size_t)n, &h->tmp_dist))) return fail(st);
     d.tri = h->tri_dev; d.reg = h->reg_dev;
     if ((st = salloc(h, 3, &d.stats))) return fail(st);
-    // launch shape: 8 warps x 2 blocks per SM by default (11 KB of scratch per warp); RBP_SK_WARPS / RBP_SK_BLOCKS_PER_SM
+    if ((st = salloc(h, 1, &d.queue))) return fail(st);
+    // launch shape: 8 warps x 3 blocks per SM by default (9 KB of scratch per warp); RBP_SK_WARPS / RBP_SK_BLOCKS_PER_SM
     // override it for tuning runs
-    int sms = 148, blocks_per_sm = 2;
+    int sms = 148, blocks_per_sm = 3;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("RBP_SK_WARPS")) h->warps = std::max(1, std::min(kSkWarps, atoi(e)));
     if (const char* e = getenv("RBP_SK_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, std::min(16, atoi(e)));
@@ -436,6 +445,7 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
 int sk_set_metric(KmSk* h, const float* tri, int bins) {
     if (!h || !tri || bins != h->d.bins) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
+    if (!sk_metric_valid(tri, bins)) { set_last_error("ground metric entries must be finite and non-negative"); return RBP_ERR_INVALID; }
     std::vector<float> metric((size_t)kSkLd * kSkLd), reg((size_t)kSkLd * kSkLd);
     sk_dense_tables(tri, bins, h->d.hp.temperature, metric.data(), reg.data());
     RBP_CUDA(cudaMemcpyAsync(h->tri_dev, metric.data(), metric.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -490,6 +500,7 @@ int sk_set_centroids(KmSk* h, const uint64_t* counts) {
 int sk_init_bounds(KmSk* h) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
+    RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
     sk_assign_kernel<true><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
     RBP_LAUNCHED();
     h->d.pending = 0;
@@ -509,6 +520,7 @@ int sk_step_local(KmSk* h) {
     RBP_CUDA(cudaMemsetAsync(d.reassigned, 0, 4, h->stream));
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * 4, h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (d.bins + 1) * 8, h->stream));
+    RBP_CUDA(cudaMemsetAsync(d.queue, 0, 8, h->stream));
     sk_step_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d);
     RBP_LAUNCHED();
     sk_accumulate_kernel<<<148 * 4, 256, 0, h->stream>>>(d);
@@ -537,6 +549,7 @@ int sk_step_finish(KmSk* h, float* drift_out, uint32_t* sizes_out, uint32_t* rea
 int sk_assign(KmSk* h, uint32_t* assign_out, float* dist_out) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
+    RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
     sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
     RBP_LAUNCHED();
     RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -617,6 +630,7 @@ int sk_timed(KmSk* h, int what, int iters, float* ms_out) {
         int st;
         if (what == 0) { st = sk_step_local(h); if (!st) st = sk_step_finish(h, nullptr, nullptr, nullptr); }
         else {
+            RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
             sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
             g_launches.fetch_add(1);
             st = cudaGetLastError() == cudaSuccess ? RBP_OK : RBP_ERR_CUDA;
@@ -638,6 +652,7 @@ int sk_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb,
         return RBP_ERR_INVALID;
     if (rbp_device_count() < 1) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
     if (n == 0) return RBP_OK;
+    if (!(temperature > 0.0f) || !sk_metric_valid(tri, bins)) { set_last_error("temperature must be positive, ground metric entries finite and non-negative"); return RBP_ERR_INVALID; }
     const size_t T = (size_t)kSkLd * kSkLd;
     std::vector<float> metric(T), reg(T);
     sk_dense_tables(tri, bins, temperature, metric.data(), reg.data());

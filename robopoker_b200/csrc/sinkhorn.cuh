@@ -6,9 +6,10 @@
 // exp terms are independent, so a half-sweep picks, per problem shape, the cheaper of two bit-identical schedules:
 //   rows:       a lane owns a target and runs its sum over the sources in a register (full lanes when the target
 //               side is wide — centroids);
-//   transposed: lanes span 32 SOURCES, the exp terms of one 32-source slab go through a [target][source] shared
+//   transposed: lanes span the SOURCES, the exp terms of one 64-source slab go through a [target][source] shared
 //               tile, and lane t then adds row t left to right (narrow target side — a point's ~11 buckets — where
 //               `rows` would leave two thirds of the warp idle in front of the 256-term loop).
+// Either way a lane has 8 independent exp chains in flight.
 // The ground metric is a dense symmetric [256][256] table (L1/L2 resident): the broadcast index picks the row, the
 // lane's index the column, so every load is one coalesced line.  exp/ln follow the contract of include/rbp.h
 // (`exp_c` / `ln_c`: fixed IEEE operation sequences with explicit fma — this file is compiled -fmad=false so nothing
@@ -20,13 +21,31 @@ namespace rbp {
 
 constexpr int kSkMaxSupport = 256;  // KMEANS_MAX_CLUSTER_COUNT (crates/pokerkit/src/lib.rs:185)
 constexpr int kSkLd = 256;          // row stride of the dense ground-metric tables
-constexpr int kSkTile = 36;         // row stride of the transposed tile (16-byte rows, conflict-free LDS.128)
+constexpr int kSkTrMax = 16;        // widest target side the transposed schedule takes
+constexpr int kSkTile = 68;         // row stride of its [target][64 sources] tile (16-byte rows, conflict-free LDS.128)
 
 // exp contract (include/rbp.h): saturating, x clamped to [ln MIN_POSITIVE, ln MAX]; k = rint(x·log2e) through the
 // 1.5·2^23 shifter; r = x − k·ln2 (two-term split); degree-5 Cephes polynomial in Horner form, all fma; 2^k applied
 // by adding k to the exponent field.
 __device__ __forceinline__ float exp_c(float x) {
     x = fminf(fmaxf(x, -87.33654f), 88.72283f);
+    const float t = __fmaf_rn(x, 1.44269504f, 12582912.0f);
+    const float kf = t - 12582912.0f;
+    float r = __fmaf_rn(kf, -0.693359375f, x);
+    r = __fmaf_rn(kf, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float y = __fmaf_rn(p, r * r, r) + 1.0f;
+    return __uint_as_float(__float_as_uint(y) + (__float_as_uint(t) << 23));
+}
+// exp_c for callers that guarantee x <= 88.72283 (every softmin / delta argument: potentials are <= -ln MIN_POSITIVE
+// and the ground metric is non-negative) — the upper clamp is then the identity
+__device__ __forceinline__ float exp_c_le(float x) {
+    x = fmaxf(x, -87.33654f);
     const float t = __fmaf_rn(x, 1.44269504f, 12582912.0f);
     const float kf = t - 12582912.0f;
     float r = __fmaf_rn(kf, -0.693359375f, x);
@@ -73,12 +92,11 @@ struct SkParams {
     float tolerance;    // 5e-4
 };
 
-// per-warp scratch in shared memory
+// per-warp scratch in shared memory (8976 B: 24 warps per SM)
 struct __align__(16) SkWarp {
     float lhs[kSkMaxSupport], rhs[kSkMaxSupport];    // potentials
-    float elhs[kSkMaxSupport], erhs[kSkMaxSupport];  // exp_c(potential): delta()'s `prev` term is last sweep's `next`
     float lnmu[kSkMaxSupport], lnnu[kSkMaxSupport];
-    float tile[32 * kSkTile];
+    float tile[kSkTrMax * kSkTile];
     uint8_t ix[kSkMaxSupport], iy[kSkMaxSupport];    // ascending support (bucket ids < 256)
     int nx, ny;
 };
@@ -86,6 +104,11 @@ struct __align__(16) SkWarp {
 // Dense symmetric ground-metric tables from `tri` in Pair::merge order (pair.rs:36-39): metric[x][y] = raw_distance
 // (0 on the diagonal, metric.rs:42-54); reg = metric / temperature element-wise — the same f32 quotient the reference
 // forms on every access (sinkhorn.rs:127-129).  Host side.
+inline bool sk_metric_valid(const float* tri, int bins) {  // distances: finite, >= 0 (exp_c_le's domain argument relies on it)
+    for (size_t t = 0; t < (size_t)bins * (bins - 1) / 2; ++t)
+        if (!(tri[t] >= 0.0f) || !(tri[t] <= 3.0e38f)) return false;
+    return true;
+}
 inline void sk_dense_tables(const float* tri, int bins, float temperature, float* metric, float* reg) {
     for (size_t i = 0; i < (size_t)kSkLd * kSkLd; ++i) { metric[i] = 0.0f; reg[i] = 0.0f; }
     for (int hi = 1; hi < bins; ++hi)
@@ -129,96 +152,112 @@ __device__ __forceinline__ float ordered_sum32(float acc, float v, float* buf, i
     return acc;
 }
 
+// softmin term max(exp(p − c), MIN_POSITIVE)  (sinkhorn.rs:118-120)
+__device__ __forceinline__ float sk_term(float p, float c) { return fmaxf(exp_c_le(p - c), kEps); }
+
+// s + Σ_{i<8} term(pot[i], col[idx[i]·ld]) left to right; MASKED: only the first m (< 8) sources exist — the other
+// slots read stale scratch and contribute an exact +0.0
+template <bool MASKED>
+__device__ __forceinline__ float sk_rows8(float s, const float* __restrict__ col, const uint8_t* __restrict__ idx, const float* __restrict__ pot, int m) {
+    const uint2 r8 = *reinterpret_cast<const uint2*>(idx);
+    const float4 pa = *reinterpret_cast<const float4*>(pot), pb = *reinterpret_cast<const float4*>(pot + 4);
+    const float c0 = __ldg(col + (int)(r8.x & 0xFFu) * kSkLd), c1 = __ldg(col + (int)((r8.x >> 8) & 0xFFu) * kSkLd);
+    const float c2 = __ldg(col + (int)((r8.x >> 16) & 0xFFu) * kSkLd), c3 = __ldg(col + (int)(r8.x >> 24) * kSkLd);
+    const float c4 = __ldg(col + (int)(r8.y & 0xFFu) * kSkLd), c5 = __ldg(col + (int)((r8.y >> 8) & 0xFFu) * kSkLd);
+    const float c6 = __ldg(col + (int)((r8.y >> 16) & 0xFFu) * kSkLd), c7 = __ldg(col + (int)(r8.y >> 24) * kSkLd);
+    float e0 = sk_term(pa.x, c0), e1 = sk_term(pa.y, c1), e2 = sk_term(pa.z, c2), e3 = sk_term(pa.w, c3);
+    float e4 = sk_term(pb.x, c4), e5 = sk_term(pb.y, c5), e6 = sk_term(pb.z, c6), e7 = sk_term(pb.w, c7);
+    if (MASKED) {
+        e1 = m > 1 ? e1 : 0.0f; e2 = m > 2 ? e2 : 0.0f; e3 = m > 3 ? e3 : 0.0f; e4 = m > 4 ? e4 : 0.0f;
+        e5 = m > 5 ? e5 : 0.0f; e6 = m > 6 ? e6 : 0.0f; e7 = 0.0f;
+    }
+    s = s + e0; s = s + e1; s = s + e2; s = s + e3; s = s + e4; s = s + e5; s = s + e6; s = s + e7;
+    return s;
+}
+
 // One Gauss-Seidel half-sweep (sinkhorn.rs:96-129 `lhs()` / `rhs()` + `delta`): for every target t
 //   next_t = ln dens_t − ln Σ_s max(exp(pot_s − reg[t][s]), MIN_POSITIVE)      (Σ sequential over the source support)
 // replaces pot_t and returns Σ_t |exp(next_t) − exp(prev_t)| (sequential over the target support).
-__device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, float* __restrict__ e_t, const float* __restrict__ lnd_t,
-                                               const uint8_t* __restrict__ idx_t, int n_t, const float* __restrict__ pot_s,
-                                               const uint8_t* __restrict__ idx_s, int n_s, float* __restrict__ tile,
-                                               const float* __restrict__ reg, int lane) {
+__device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const float* __restrict__ lnd_t, const uint8_t* __restrict__ idx_t, int n_t,
+                                               const float* __restrict__ pot_s, const uint8_t* __restrict__ idx_s, int n_s,
+                                               float* __restrict__ tile, const float* __restrict__ reg, int lane) {
     float err = 0.0f;
-    // issue-slot model: rows = ceil(n_t/32)·n_s exp steps; transposed = n_t·ceil(n_s/32) exp steps + the row adds
+    // issue-slot model: rows = ceil(n_t/32)·n_s exp steps; transposed = ceil4(n_t)·ceil(n_s/32) exp steps + the row adds
+    const int n_t4 = (n_t + 3) & ~3;
     const int cost_rows = ((n_t + 31) >> 5) * n_s;
-    const int cost_tr = n_t * ((n_s + 31) >> 5) + (n_s >> 4) + 1;
-    if (n_t <= 32 && cost_tr < cost_rows) {
+    const int cost_tr = n_t4 * ((n_s + 31) >> 5) + (n_s >> 4) + 2;
+    if (n_t <= kSkTrMax && cost_tr < cost_rows) {
         float s = 0.0f;  // lane t: running sum of target t
-        const int n_t4 = (n_t + 3) & ~3;  // rows n_t..n_t4-1 of the tile are written (stale bucket ids, valid table rows) and never read
-        for (int s0 = 0; s0 < n_s; s0 += 32) {
-            const int si = s0 + lane;
-            const bool live = si < n_s;
-            const float ps = live ? pot_s[si] : 0.0f;
-            const float* __restrict__ col = reg + (live ? (int)idx_s[si] : 0);
-            uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t);
-            float c0 = __ldg(col + (int)r4.x * kSkLd), c1 = __ldg(col + (int)r4.y * kSkLd);
-            float c2 = __ldg(col + (int)r4.z * kSkLd), c3 = __ldg(col + (int)r4.w * kSkLd);
-            for (int t = 0; t < n_t4; t += 4) {
-                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-                if (t + 4 < n_t4) {  // next group's table loads run under this group's arithmetic
-                    r4 = *reinterpret_cast<const uchar4*>(idx_t + t + 4);
-                    m0 = __ldg(col + (int)r4.x * kSkLd); m1 = __ldg(col + (int)r4.y * kSkLd);
-                    m2 = __ldg(col + (int)r4.z * kSkLd); m3 = __ldg(col + (int)r4.w * kSkLd);
+        for (int s0 = 0; s0 < n_s; s0 += 64) {
+            const bool wide = n_s - s0 > 32;          // the slab's second half holds sources (warp-uniform)
+            const int sa = s0 + lane, sb = sa + 32;
+            const bool la = sa < n_s, lb = sb < n_s;
+            const float pa = la ? pot_s[sa] : 0.0f, pb = lb ? pot_s[sb] : 0.0f;
+            const float* __restrict__ cola = reg + (la ? (int)idx_s[sa] : 0);
+            const float* __restrict__ colb = reg + (lb ? (int)idx_s[sb] : 0);
+            // rows n_t..n_t4-1 of the tile are written from stale bucket ids (valid table rows) and never read
+            if (wide) {
+                for (int t = 0; t < n_t4; t += 4) {
+                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t + t);
+                    const int o0 = (int)r4.x * kSkLd, o1 = (int)r4.y * kSkLd, o2 = (int)r4.z * kSkLd, o3 = (int)r4.w * kSkLd;
+                    const float a0 = __ldg(cola + o0), a1 = __ldg(cola + o1), a2 = __ldg(cola + o2), a3 = __ldg(cola + o3);
+                    const float b0 = __ldg(colb + o0), b1 = __ldg(colb + o1), b2 = __ldg(colb + o2), b3 = __ldg(colb + o3);
+                    const float e0 = sk_term(pa, a0), e1 = sk_term(pa, a1), e2 = sk_term(pa, a2), e3 = sk_term(pa, a3);
+                    const float f0 = sk_term(pb, b0), f1 = sk_term(pb, b1), f2 = sk_term(pb, b2), f3 = sk_term(pb, b3);
+                    float* __restrict__ w = tile + t * kSkTile + lane;
+                    w[0] = la ? e0 : 0.0f; w[kSkTile] = la ? e1 : 0.0f; w[2 * kSkTile] = la ? e2 : 0.0f; w[3 * kSkTile] = la ? e3 : 0.0f;
+                    w[32] = lb ? f0 : 0.0f; w[kSkTile + 32] = lb ? f1 : 0.0f; w[2 * kSkTile + 32] = lb ? f2 : 0.0f; w[3 * kSkTile + 32] = lb ? f3 : 0.0f;
                 }
-                const float e0 = fmaxf(exp_c(ps - c0), kEps), e1 = fmaxf(exp_c(ps - c1), kEps);
-                const float e2 = fmaxf(exp_c(ps - c2), kEps), e3 = fmaxf(exp_c(ps - c3), kEps);
-                tile[(t + 0) * kSkTile + lane] = live ? e0 : 0.0f;
-                tile[(t + 1) * kSkTile + lane] = live ? e1 : 0.0f;
-                tile[(t + 2) * kSkTile + lane] = live ? e2 : 0.0f;
-                tile[(t + 3) * kSkTile + lane] = live ? e3 : 0.0f;
-                c0 = m0; c1 = m1; c2 = m2; c3 = m3;
+            } else {
+                for (int t = 0; t < n_t4; t += 4) {
+                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t + t);
+                    const float a0 = __ldg(cola + (int)r4.x * kSkLd), a1 = __ldg(cola + (int)r4.y * kSkLd);
+                    const float a2 = __ldg(cola + (int)r4.z * kSkLd), a3 = __ldg(cola + (int)r4.w * kSkLd);
+                    const float e0 = sk_term(pa, a0), e1 = sk_term(pa, a1), e2 = sk_term(pa, a2), e3 = sk_term(pa, a3);
+                    float* __restrict__ w = tile + t * kSkTile + lane;
+                    w[0] = la ? e0 : 0.0f; w[kSkTile] = la ? e1 : 0.0f; w[2 * kSkTile] = la ? e2 : 0.0f; w[3 * kSkTile] = la ? e3 : 0.0f;
+                }
             }
             __syncwarp();
-            if (lane < n_t) {
+            if (lane < n_t) {  // dead sources hold +0.0: an exact no-op on a non-negative sum
                 const float4* __restrict__ row = reinterpret_cast<const float4*>(tile + lane * kSkTile);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 w = row[q];
                     s = s + w.x; s = s + w.y; s = s + w.z; s = s + w.w;
                 }
+                if (wide) {
+#pragma unroll
+                    for (int q = 8; q < 16; ++q) {
+                        const float4 w = row[q];
+                        s = s + w.x; s = s + w.y; s = s + w.z; s = s + w.w;
+                    }
+                }
             }
             __syncwarp();
         }
         float v = 0.0f;
         if (lane < n_t) {
+            const float prev = pot_t[lane];
             const float nv = lnd_t[lane] - ln_c(s);
-            const float en = exp_c(nv);
-            v = fabsf(en - e_t[lane]);
-            e_t[lane] = en;
+            v = fabsf(exp_c_le(nv) - exp_c_le(prev));
             pot_t[lane] = nv;
         }
         err = ordered_sum32(err, v, tile, lane);
     } else {
-        const int n_s4 = n_s & ~3;
+        const int n_s8 = n_s & ~7;
         for (int t0 = 0; t0 < n_t; t0 += 32) {
             const int t = t0 + lane;
             const bool live = t < n_t;
             const float* __restrict__ col = reg + (live ? (int)idx_t[t] : 0);
             float s = 0.0f;
-            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-            if (n_s4) {
-                const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_s);
-                c0 = __ldg(col + (int)r4.x * kSkLd); c1 = __ldg(col + (int)r4.y * kSkLd);
-                c2 = __ldg(col + (int)r4.z * kSkLd); c3 = __ldg(col + (int)r4.w * kSkLd);
-            }
-            for (int q = 0; q < n_s4; q += 4) {
-                const float4 p4 = *reinterpret_cast<const float4*>(pot_s + q);
-                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-                if (q + 4 < n_s4) {  // next group's table loads run under this group's arithmetic
-                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_s + q + 4);
-                    m0 = __ldg(col + (int)r4.x * kSkLd); m1 = __ldg(col + (int)r4.y * kSkLd);
-                    m2 = __ldg(col + (int)r4.z * kSkLd); m3 = __ldg(col + (int)r4.w * kSkLd);
-                }
-                const float e0 = fmaxf(exp_c(p4.x - c0), kEps), e1 = fmaxf(exp_c(p4.y - c1), kEps);
-                const float e2 = fmaxf(exp_c(p4.z - c2), kEps), e3 = fmaxf(exp_c(p4.w - c3), kEps);
-                s = s + e0; s = s + e1; s = s + e2; s = s + e3;
-                c0 = m0; c1 = m1; c2 = m2; c3 = m3;
-            }
-            for (int q = n_s4; q < n_s; ++q) s = s + fmaxf(exp_c(pot_s[q] - __ldg(col + (int)idx_s[q] * kSkLd)), kEps);
+            for (int q = 0; q < n_s8; q += 8) s = sk_rows8<false>(s, col, idx_s + q, pot_s + q, 8);
+            if (n_s8 < n_s) s = sk_rows8<true>(s, col, idx_s + n_s8, pot_s + n_s8, n_s - n_s8);
             float v = 0.0f;
             if (live) {
+                const float prev = pot_t[t];
                 const float nv = lnd_t[t] - ln_c(s);
-                const float en = exp_c(nv);
-                v = fabsf(en - e_t[t]);
-                e_t[t] = en;
+                v = fabsf(exp_c_le(nv) - exp_c_le(prev));
                 pot_t[t] = nv;
             }
             err = ordered_sum32(err, v, tile, lane);
@@ -233,14 +272,13 @@ __device__ __forceinline__ float sk_solve(SkWarp& w, const float* __restrict__ m
                                           unsigned long long* __restrict__ stats = nullptr) {
     const int nx = w.nx, ny = w.ny;
     const float lx0 = ln_c(1.0f / (float)nx), ly0 = ln_c(1.0f / (float)ny);  // Phi::uniform (phi.rs:25-30)
-    const float ex0 = exp_c(lx0), ey0 = exp_c(ly0);
-    for (int i = lane; i < nx; i += 32) { w.lhs[i] = lx0; w.elhs[i] = ex0; }
-    for (int j = lane; j < ny; j += 32) { w.rhs[j] = ly0; w.erhs[j] = ey0; }
+    for (int i = lane; i < nx; i += 32) w.lhs[i] = lx0;
+    for (int j = lane; j < ny; j += 32) w.rhs[j] = ly0;
     __syncwarp();
     int sweeps = 0;
     for (int t = 0; t < hp.iterations; ++t) {
-        const float lerr = sk_half_sweep(w.lhs, w.elhs, w.lnmu, w.ix, nx, w.rhs, w.iy, ny, w.tile, reg, lane);
-        const float rerr = sk_half_sweep(w.rhs, w.erhs, w.lnnu, w.iy, ny, w.lhs, w.ix, nx, w.tile, reg, lane);  // against the NEW lhs
+        const float lerr = sk_half_sweep(w.lhs, w.lnmu, w.ix, nx, w.rhs, w.iy, ny, w.tile, reg, lane);
+        const float rerr = sk_half_sweep(w.rhs, w.lnnu, w.iy, ny, w.lhs, w.ix, nx, w.tile, reg, lane);  // against the NEW lhs
         ++sweeps;
         if (lerr + rerr < hp.tolerance) break;
     }

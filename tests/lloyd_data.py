@@ -28,3 +28,18 @@ def flop_histograms(n, bins, seed=0, draws=47, spread=3.0):
     pts = np.zeros((n, bins), dtype=np.uint8)
     np.add.at(pts, (np.repeat(np.arange(n), draws), vals.ravel()), 1)
     return pts
+
+
+def flop_mixture_histograms(n, bins=256, comps=200, alpha=0.3, seed=0, draws=47):
+    """`draws` samples per point from a `comps`-component Dirichlet(alpha) mixture over `bins`
+    next-street clusters.  alpha=0.3 is the survey's value (mean support ~34); alpha=0.02 matches the mean support
+    (~11) measured on real flop projections (profiles/r1g_pipeline_blueprint.json)."""
+    rng = np.random.default_rng(seed)
+    comp = rng.dirichlet(np.full(bins, alpha), size=comps)
+    z = rng.integers(0, comps, n)
+    pts = np.zeros((n, bins), dtype=np.uint8)
+    for c in range(comps):
+        rows = np.flatnonzero(z == c)
+        if len(rows):
+            pts[rows] = rng.multinomial(draws, comp[c], size=len(rows)).astype(np.uint8)
+    return pts

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary benchmark (BASELINE.json configs[2], flop abstraction layer): the Sinkhorn N x K assignment sweep and one
-Elkan step on synthetic flop histograms (47 draws over 256 turn clusters, mean support ~11) against K centroids,
+Elkan step on synthetic flop histograms (47 draws from a Dirichlet mixture over 256 turn clusters) against K centroids,
 reported as OT solves/s and exp terms/s against the FP32-issue ceiling, next to the oracle on the host cores.
 
     python tools/bench_sinkhorn.py --n 20000 --k 200
@@ -29,16 +29,19 @@ def main():
     p.add_argument("--sweeps", type=int, default=2, help="timed N x K assignment sweeps")
     p.add_argument("--steps", type=int, default=1, help="timed Elkan steps")
     p.add_argument("--cpu-pairs", type=int, default=2048, help="point-centroid solves for the oracle's bounded sample (0 = skip)")
+    p.add_argument("--alpha", type=float, default=0.02,
+                   help="Dirichlet concentration of the synthetic mixture: 0.02 = mean point support ~11 (as measured on real flop "
+                        "projections), 0.3 = SURVEY 8d config 3 (support ~34)")
     p.add_argument("--tag", default="")
     args = p.parse_args()
     import numpy as np
-    from lloyd_data import flop_histograms, synthetic_metric
+    from lloyd_data import flop_mixture_histograms, synthetic_metric
 
     import robopoker_b200 as rbp
 
     fadd = ctypes.c_float()
     rbp.load_library().rbp_measure_fadd_peak(ctypes.byref(fadd))
-    pts = flop_histograms(args.n, args.bins, seed=0)
+    pts = flop_mixture_histograms(args.n, args.bins, comps=args.k, alpha=args.alpha, seed=0)
     tri = synthetic_metric(args.bins, 0)
     t0 = time.perf_counter()
     g = rbp.lloyd.Layer(pts, args.k, metric=tri)
@@ -56,7 +59,7 @@ def main():
     st_solves, st_sweeps, st_terms = (x / args.steps for x in g.sinkhorn_stats(reset=True))
     counts, _ = g.future()
     peak_terms = fadd.value * 1e12 / FMA_PIPE_PER_TERM
-    line = {"bench": "lloyd_flop_sinkhorn", "tag": args.tag, "n": args.n, "k": args.k, "bins": args.bins,
+    line = {"bench": "lloyd_flop_sinkhorn", "tag": args.tag, "n": args.n, "k": args.k, "bins": args.bins, "alpha": args.alpha,
             "mean_point_support": float((pts > 0).sum(axis=1).mean()), "mean_centroid_support": float((counts > 0).sum(axis=1).mean()),
             "create_self_terms_s": t_create, "init_pp_s": t_pp, "init_pp_solves": s_pp[0], "init_bounds_s": t_bounds,
             "init_bounds_solves_per_s": args.n * args.k / t_bounds,
@@ -66,7 +69,7 @@ def main():
             "roofline": {"bound": "fp32-issue", "kernel": "sk_assign_kernel", "achieved": terms / (ms_assign * 1e-3) / 1e9, "peak": peak_terms / 1e9,
                          "unit": "G exp terms/s", "frac": terms / (ms_assign * 1e-3) / peak_terms,
                          "note": f"peak = measured FADD issue rate {fadd.value:.1f} T lane-ops/s / {FMA_PIPE_PER_TERM} FMA-pipe instructions per exp term"},
-            "launch": {"RBP_SK_WARPS": os.environ.get("RBP_SK_WARPS", "8"), "RBP_SK_BLOCKS_PER_SM": os.environ.get("RBP_SK_BLOCKS_PER_SM", "2")}}
+            "launch": {"RBP_SK_WARPS": os.environ.get("RBP_SK_WARPS", "8"), "RBP_SK_BLOCKS_PER_SM": os.environ.get("RBP_SK_BLOCKS_PER_SM", "3")}}
     if args.cpu_pairs:
         from oracle import binding as oracle
 
