@@ -19,6 +19,7 @@
 namespace rbp {
 
 constexpr int kSkWarps = 8;          // max warps (OT problems) per block; the launch picks blockDim = 32 x warps
+constexpr int kSkMinBlocks = 4;       // register budget 64: ptxas serialises the 8 exp chains without a budget (see profiles/r1n)
 constexpr int kPtMax = 64;           // max support of a point (flop children: 47, crates/deuce/src/street.rs:120-126)
 
 struct SkDev {
@@ -59,63 +60,65 @@ __device__ __forceinline__ int64_t next_point(const SkDev& d, int lane) {
     if (lane == 0) i = atomicAdd(d.queue, 1ull);
     return (int64_t)__shfl_sync(0xFFFFFFFFu, i, 0);
 }
-__device__ __forceinline__ void load_point(const SkDev& d, int64_t i, uint8_t* idx, float* lnd, int* n_out, int lane) {
+__device__ __forceinline__ int load_point(const SkDev& d, int64_t i, uint8_t* idx, float* lnd, int lane) {
     const int n = d.p_n[i];
     const float w = (float)d.p_w[i];
     for (int t = lane; t < n; t += 32) {
         idx[t] = d.p_idx[(size_t)i * kPtMax + t];
         lnd[t] = ln_c((float)d.p_cnt[(size_t)i * kPtMax + t] / w);
     }
-    *n_out = n;
     __syncwarp();
+    return n;
 }
-__device__ __forceinline__ void load_centroid(const unsigned long long* __restrict__ counts, int bins, uint8_t* idx, float* lnd, int* n_out, int lane) {
+__device__ __forceinline__ int load_centroid(const unsigned long long* __restrict__ counts, int bins, uint8_t* idx, float* lnd, int lane) {
     const float w = (float)counts[bins];
-    *n_out = sk_load_side([&](int b) { return (float)counts[b]; }, w, bins, idx, lnd, lane);
+    return sk_load_side([&](int b) { return (float)counts[b]; }, w, bins, idx, lnd, lane);
+}
+template <class W>
+__device__ __forceinline__ W& warp_scratch() {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return reinterpret_cast<W*>(smem_raw)[threadIdx.x >> 5];
 }
 
 // OT(h,h) for points / for a centroid table
-__global__ void __launch_bounds__(kSkWarps * 32) sk_self_points_kernel(SkDev d) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_self_points_kernel(SkDev d) {
+    SkPoint& w = warp_scratch<SkPoint>();
     const int lane = threadIdx.x & 31;
     for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        load_point(d, i, w.ix, w.lnmu, &w.nx, lane);
-        load_point(d, i, w.iy, w.lnnu, &w.ny, lane);
-        const float c = sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats);
+        w.n_a = load_point(d, i, w.idx_a, w.lnd_a, lane);
+        w.n_b = load_point(d, i, w.idx_b, w.lnd_b, lane);
+        const float c = sk_solve(w.a(), w.b(), w.tile, d.tri, d.reg, d.hp, lane, d.stats);
         if (lane == 0) d.p_self[i] = c;
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(kSkWarps * 32) sk_self_centroids_kernel(SkDev d, const unsigned long long* __restrict__ counts, float* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_self_centroids_kernel(SkDev d, const unsigned long long* __restrict__ counts, float* __restrict__ out) {
+    SkWide& w = warp_scratch<SkWide>();
     const int lane = threadIdx.x & 31;
     for (int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < d.k; j += gridDim.x * (blockDim.x >> 5)) {
         const unsigned long long* c = counts + (size_t)j * (d.bins + 1);
-        load_centroid(c, d.bins, w.ix, w.lnmu, &w.nx, lane);
-        load_centroid(c, d.bins, w.iy, w.lnnu, &w.ny, lane);
-        const float v = sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats);
+        w.n_a = load_centroid(c, d.bins, w.idx_a, w.lnd_a, lane);
+        w.n_b = load_centroid(c, d.bins, w.idx_b, w.lnd_b, lane);
+        const float v = sk_solve(w.a(), w.b(), w.tile, d.tri, d.reg, d.hp, lane, d.stats);
         if (lane == 0) out[j] = v;
         __syncwarp();
     }
 }
 
 // centroid-vs-centroid divergences: out[t] = divergence(A[ia[t]], B[ib[t]])  (pairwises, drift, metric)
-__global__ void __launch_bounds__(kSkWarps * 32)
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks)
 sk_centroid_pairs_kernel(SkDev d, const unsigned long long* __restrict__ A, const float* __restrict__ selfA, const unsigned long long* __restrict__ B,
                          const float* __restrict__ selfB, int mode, int total, float* __restrict__ out) {
     // mode 0: all (i, j) of the K x K pairwise table (diagonal = 0);  mode 1: drift, t -> (t, t)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+    SkWide& w = warp_scratch<SkWide>();
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += gridDim.x * (blockDim.x >> 5)) {
         const int i = mode == 0 ? t / d.k : t, j = mode == 0 ? t % d.k : t;
         float v = 0.0f;
         if (!(mode == 0 && i == j)) {  // elkan.rs:91-93 pairwise(i, i) = 0
-            load_centroid(A + (size_t)i * (d.bins + 1), d.bins, w.ix, w.lnmu, &w.nx, lane);
-            load_centroid(B + (size_t)j * (d.bins + 1), d.bins, w.iy, w.lnnu, &w.ny, lane);
-            v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), selfA[i], selfB[j]);
+            w.n_a = load_centroid(A + (size_t)i * (d.bins + 1), d.bins, w.idx_a, w.lnd_a, lane);
+            w.n_b = load_centroid(B + (size_t)j * (d.bins + 1), d.bins, w.idx_b, w.lnd_b, lane);
+            v = sk_divergence(sk_solve(w.a(), w.b(), w.tile, d.tri, d.reg, d.hp, lane, d.stats), selfA[i], selfB[j]);
         }
         if (lane == 0) out[t] = v;
         __syncwarp();
@@ -155,16 +158,15 @@ __global__ void sk_metric_kernel(const float* __restrict__ pair, int k, float* _
 }
 
 // k-means++ potentials: pot_i = min(pot_i, divergence(x_pick, h_i)^2)   (layer.rs:166-178)
-__global__ void __launch_bounds__(kSkWarps * 32) sk_pp_update_kernel(SkDev d, float* __restrict__ pot, const int64_t* __restrict__ pick, int first) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_pp_update_kernel(SkDev d, float* __restrict__ pot, const int64_t* __restrict__ pick, int first) {
+    SkPoint& w = warp_scratch<SkPoint>();
     const int lane = threadIdx.x & 31;
     for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < d.n; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         if (first) { if (lane == 0) pot[i] = 1.0f; continue; }
         const int64_t pk = *pick;
-        load_point(d, pk, w.ix, w.lnmu, &w.nx, lane);
-        load_point(d, i, w.iy, w.lnnu, &w.ny, lane);
-        const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.p_self[pk], d.p_self[i]);
+        w.n_a = load_point(d, pk, w.idx_a, w.lnd_a, lane);
+        w.n_b = load_point(d, i, w.idx_b, w.lnd_b, lane);
+        const float dist = sk_divergence(sk_solve(w.a(), w.b(), w.tile, d.tri, d.reg, d.hp, lane, d.stats), d.p_self[pk], d.p_self[i]);
         if (lane == 0) {
             const float d2 = dist * dist;
             float p = pot[i];
@@ -189,17 +191,17 @@ __global__ void sk_set_centroid_kernel(SkDev d, const int64_t* __restrict__ pick
 
 // naive argmin over all centroids with distance(c_j, x): init_bounds (elkan.rs:39-47) and lookup (layer.rs:44-60)
 template <bool INIT_BOUNDS>
-__global__ void __launch_bounds__(kSkWarps * 32) sk_assign_kernel(SkDev d, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_assign_kernel(SkDev d, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist) {
+    SkPoint& w = warp_scratch<SkPoint>();
     const int lane = threadIdx.x & 31;
     for (int64_t i = next_point(d, lane); i < d.n; i = next_point(d, lane)) {
         float best = 0.0f;
         int bestj = -1;
+        w.n_a = load_point(d, i, w.idx_a, w.lnd_a, lane);                                             // nu = point, once
+        const float self_i = d.p_self[i];
         for (int j = 0; j < d.k; ++j) {
-            load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.ix, w.lnmu, &w.nx, lane);  // mu = centroid
-            load_point(d, i, w.iy, w.lnnu, &w.ny, lane);                                              // nu = point
-            const float dist = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.c_self[j], d.p_self[i]);
+            w.n_b = load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.idx_b, w.lnd_b, lane);  // mu = centroid
+            const float dist = sk_divergence(sk_solve(w.b(), w.a(), w.tile, d.tri, d.reg, d.hp, lane, d.stats), d.c_self[j], self_i);
             if (bestj < 0 || dist < best) { best = dist; bestj = j; }
             __syncwarp();
         }
@@ -214,9 +216,8 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_assign_kernel(SkDev d, uint3
 }
 
 // one Elkan step, point side (elkan.rs:153-164): a warp owns a point; all tests are warp-uniform
-__global__ void __launch_bounds__(kSkWarps * 32) sk_step_kernel(SkDev d) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_step_kernel(SkDev d) {
+    SkPoint& w = warp_scratch<SkPoint>();
     const int lane = threadIdx.x & 31;
     for (int64_t i = next_point(d, lane); i < d.n; i = next_point(d, lane)) {
         uint32_t c = d.assign[i];
@@ -231,10 +232,11 @@ __global__ void __launch_bounds__(kSkWarps * 32) sk_step_kernel(SkDev d) {
             __syncwarp();
         }
         if (u > d.mid[c]) {  // step_elkan filter
+            w.n_a = load_point(d, i, w.idx_a, w.lnd_a, lane);  // mu = point, once
+            const float self_i = d.p_self[i];
             auto dist_to = [&](int j) {  // distance(x, c_j): mu = point, nu = centroid
-                load_point(d, i, w.ix, w.lnmu, &w.nx, lane);
-                load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.iy, w.lnnu, &w.ny, lane);
-                const float v = sk_divergence(sk_solve(w, d.tri, d.reg, d.hp, lane, d.stats), d.p_self[i], d.c_self[j]);
+                w.n_b = load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.idx_b, w.lnd_b, lane);
+                const float v = sk_divergence(sk_solve(w.a(), w.b(), w.tile, d.tri, d.reg, d.hp, lane, d.stats), self_i, d.c_self[j]);
                 __syncwarp();
                 return v;
             };
@@ -281,13 +283,12 @@ __global__ void sk_materialize_kernel(SkDev d) {
 }
 
 // generic batch: out[t] = divergence(A[ia[t]], B[ib[t]]) over dense u32 histograms
-__global__ void __launch_bounds__(kSkWarps * 32)
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks)
 sk_batch_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, int bins, const int32_t* __restrict__ ia, const int32_t* __restrict__ ib,
                 int64_t n, int mode, const float* __restrict__ selfA, const float* __restrict__ selfB, const float* __restrict__ tri,
                 const float* __restrict__ reg, SkParams hp, float* __restrict__ out) {
     // mode 0: self costs of A (n = |A|); mode 1: divergences of the listed pairs
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkWarp& w = reinterpret_cast<SkWarp*>(smem_raw)[threadIdx.x >> 5];
+    SkWide& w = warp_scratch<SkWide>();
     const int lane = threadIdx.x & 31;
     for (int64_t t = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         const int a = mode == 0 ? (int)t : ia[t], b = mode == 0 ? (int)t : ib[t];
@@ -300,9 +301,9 @@ sk_batch_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, 
             for (int s = 16; s > 0; s >>= 1) { sa += __shfl_xor_sync(0xFFFFFFFFu, sa, s); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, s); }
             wa = (float)sa; wb = (float)sb;
         }
-        w.nx = sk_load_side([&](int q) { return (float)ha[q]; }, wa, bins, w.ix, w.lnmu, lane);
-        w.ny = sk_load_side([&](int q) { return (float)hb[q]; }, wb, bins, w.iy, w.lnnu, lane);
-        const float c = sk_solve(w, tri, reg, hp, lane);
+        w.n_a = sk_load_side([&](int q) { return (float)ha[q]; }, wa, bins, w.idx_a, w.lnd_a, lane);
+        w.n_b = sk_load_side([&](int q) { return (float)hb[q]; }, wb, bins, w.idx_b, w.lnd_b, lane);
+        const float c = sk_solve(w.a(), w.b(), w.tile, tri, reg, hp, lane);
         if (lane == 0) out[t] = mode == 0 ? c : sk_divergence(c, selfA[a], selfB[b]);
         __syncwarp();
     }
@@ -327,7 +328,7 @@ struct KmSk : rbp_kmeans {
     uint32_t* tmp_assign = nullptr;
     float* tmp_dist = nullptr;
     int nb = 0, grid = 0, warps = kSkWarps, threads = kSkWarps * 32;
-    size_t smem = 0;
+    size_t smem = 0, smem_wide = 0;  // dynamic shared memory of the point-class / centroid-class kernels
     bool have_metric = false, have_centroids = false, have_bounds = false;
 };
 
@@ -361,7 +362,7 @@ int supload(KmSk* h, const std::vector<T>& v, const T** out) {
     return RBP_OK;
 }
 int centroid_selfs(KmSk* h, const unsigned long long* counts, float* out) {
-    sk_self_centroids_kernel<<<std::min(h->grid, (h->d.k + h->warps - 1) / h->warps), h->threads, h->smem, h->stream>>>(h->d, counts, out);
+    sk_self_centroids_kernel<<<std::min(h->grid, (h->d.k + h->warps - 1) / h->warps), h->threads, h->smem_wide, h->stream>>>(h->d, counts, out);
     RBP_LAUNCHED();
     return RBP_OK;
 }
@@ -423,20 +424,21 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     d.tri = h->tri_dev; d.reg = h->reg_dev;
     if ((st = salloc(h, 3, &d.stats))) return fail(st);
     if ((st = salloc(h, 1, &d.queue))) return fail(st);
-    // launch shape: 8 warps x 3 blocks per SM by default (9 KB of scratch per warp); RBP_SK_WARPS / RBP_SK_BLOCKS_PER_SM
+    // launch shape: 8 warps x 3 blocks per SM by default (5.2 KB of scratch per warp for point problems); RBP_SK_WARPS / RBP_SK_BLOCKS_PER_SM
     // override it for tuning runs
     int sms = 148, blocks_per_sm = 3;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("RBP_SK_WARPS")) h->warps = std::max(1, std::min(kSkWarps, atoi(e)));
     if (const char* e = getenv("RBP_SK_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, std::min(16, atoi(e)));
     h->threads = h->warps * 32;
-    h->smem = h->warps * sizeof(SkWarp);
+    h->smem = h->warps * sizeof(SkPoint);
+    h->smem_wide = h->warps * sizeof(SkWide);
     h->grid = sms * blocks_per_sm;
     const void* kernels[] = {(const void*)sk_self_points_kernel, (const void*)sk_self_centroids_kernel, (const void*)sk_centroid_pairs_kernel,
                              (const void*)sk_pp_update_kernel, (const void*)sk_assign_kernel<true>, (const void*)sk_assign_kernel<false>,
                              (const void*)sk_step_kernel, (const void*)sk_batch_kernel};
     for (const void* f : kernels)
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess) return fail(RBP_ERR_CUDA);
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_wide) != cudaSuccess) return fail(RBP_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
     *out = h;
     return RBP_OK;
@@ -513,7 +515,7 @@ int sk_step_local(KmSk* h) {
     if (!h->have_bounds) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
     SkDev& d = h->d;
-    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem_wide, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
     RBP_LAUNCHED();
     sk_mid_kernel<<<(d.k + 127) / 128, 128, 0, h->stream>>>(d.pair, d.k, d.mid);
     RBP_LAUNCHED();
@@ -534,7 +536,7 @@ int sk_step_finish(KmSk* h, float* drift_out, uint32_t* sizes_out, uint32_t* rea
     int st = centroid_selfs(h, d.acc, d.new_self);
     if (st) return st;
     // drift_j = distance(new_j, old_j)  (elkan.rs:107-109)
-    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.acc, d.new_self, d.ccount, d.c_self, 1, d.k, d.drift);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem_wide, h->stream>>>(d, d.acc, d.new_self, d.ccount, d.c_self, 1, d.k, d.drift);
     RBP_LAUNCHED();
     std::swap(d.acc, d.ccount);
     std::swap(d.new_self, d.c_self);
@@ -576,7 +578,7 @@ int sk_metric(KmSk* h, float* tri_out) {
     SkDev& d = h->d;
     const int total = d.k * (d.k - 1) / 2;
     if (total == 0) return RBP_OK;
-    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
+    sk_centroid_pairs_kernel<<<h->grid, h->threads, h->smem_wide, h->stream>>>(d, d.ccount, d.c_self, d.ccount, d.c_self, 0, d.k * d.k, d.pair);
     RBP_LAUNCHED();
     sk_metric_kernel<<<1, 256, 0, h->stream>>>(d.pair, d.k, h->tri_out);
     RBP_LAUNCHED();
@@ -669,7 +671,7 @@ int sk_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb,
     RBP_CUDA(cudaMemcpy(dib, ib, n * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dtri, metric.data(), T * 4, cudaMemcpyHostToDevice));
     RBP_CUDA(cudaMemcpy(dreg, reg.data(), T * 4, cudaMemcpyHostToDevice));
-    const size_t smem = kSkWarps * sizeof(SkWarp);
+    const size_t smem = kSkWarps * sizeof(SkWide);
     RBP_CUDA(cudaFuncSetAttribute(sk_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SkParams hp{temperature, iterations, tolerance};
     const int grid = 148 * 2;

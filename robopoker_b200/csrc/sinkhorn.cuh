@@ -6,10 +6,12 @@
 // exp terms are independent, so a half-sweep picks, per problem shape, the cheaper of two bit-identical schedules:
 //   rows:       a lane owns a target and runs its sum over the sources in a register (full lanes when the target
 //               side is wide — centroids);
-//   transposed: lanes span the SOURCES, the exp terms of one 64-source slab go through a [target][source] shared
+//   transposed: lanes span the SOURCES, the exp terms of one 32-source slab go through a [target][source] shared
 //               tile, and lane t then adds row t left to right (narrow target side — a point's ~11 buckets — where
 //               `rows` would leave two thirds of the warp idle in front of the 256-term loop).
-// Either way a lane has 8 independent exp chains in flight.
+// Either way a lane has up to 8 independent exp chains in flight.  Scratch is sized per problem class (a point side
+// holds <= 64 buckets): 5.2 KB per warp for point problems, so 24-32 warps per SM leave the L1 large enough to keep the
+// table rows in use resident (the sweeps re-read the same nx x ny entries ~230 times per solve).
 // The ground metric is a dense symmetric [256][256] table (L1/L2 resident): the broadcast index picks the row, the
 // lane's index the column, so every load is one coalesced line.  exp/ln follow the contract of include/rbp.h
 // (`exp_c` / `ln_c`: fixed IEEE operation sequences with explicit fma — this file is compiled -fmad=false so nothing
@@ -22,7 +24,7 @@ namespace rbp {
 constexpr int kSkMaxSupport = 256;  // KMEANS_MAX_CLUSTER_COUNT (crates/pokerkit/src/lib.rs:185)
 constexpr int kSkLd = 256;          // row stride of the dense ground-metric tables
 constexpr int kSkTrMax = 16;        // widest target side the transposed schedule takes
-constexpr int kSkTile = 68;         // row stride of its [target][64 sources] tile (16-byte rows, conflict-free LDS.128)
+constexpr int kSkTile = 36;         // row stride of its [target][32 sources] tile (16-byte rows, conflict-free LDS.128)
 
 // exp contract (include/rbp.h): saturating, x clamped to [ln MIN_POSITIVE, ln MAX]; k = rint(x·log2e) through the
 // 1.5·2^23 shifter; r = x − k·ln2 (two-term split); degree-5 Cephes polynomial in Horner form, all fma; 2^k applied
@@ -92,14 +94,26 @@ struct SkParams {
     float tolerance;    // 5e-4
 };
 
-// per-warp scratch in shared memory (8976 B: 24 warps per SM)
-struct __align__(16) SkWarp {
-    float lhs[kSkMaxSupport], rhs[kSkMaxSupport];    // potentials
-    float lnmu[kSkMaxSupport], lnnu[kSkMaxSupport];
-    float tile[kSkTrMax * kSkTile];
-    uint8_t ix[kSkMaxSupport], iy[kSkMaxSupport];    // ascending support (bucket ids < 256)
-    int nx, ny;
+// One side of an OT problem as it sits in the warp scratch: potential, ln(density), ascending support
+struct SkSide {
+    float* pot;
+    const float* lnd;
+    const uint8_t* idx;
+    int n;
 };
+// per-warp scratch in shared memory: slot A holds <= NA buckets (points: 64), slot B <= NB (centroids: 256).
+// <64,256> = 5200 B, <256,256> = 6928 B.
+template <int NA, int NB>
+struct __align__(16) SkScratch {
+    float pot_a[NA], lnd_a[NA], pot_b[NB], lnd_b[NB];
+    float tile[kSkTrMax * kSkTile];
+    uint8_t idx_a[NA], idx_b[NB];  // bucket ids < 256
+    int n_a, n_b;
+    __device__ __forceinline__ SkSide a() { return SkSide{pot_a, lnd_a, idx_a, n_a}; }
+    __device__ __forceinline__ SkSide b() { return SkSide{pot_b, lnd_b, idx_b, n_b}; }
+};
+using SkPoint = SkScratch<64, kSkMaxSupport>;             // point x centroid, point x point
+using SkWide = SkScratch<kSkMaxSupport, kSkMaxSupport>;   // centroid x centroid, generic batches
 
 // Dense symmetric ground-metric tables from `tri` in Pair::merge order (pair.rs:36-39): metric[x][y] = raw_distance
 // (0 on the diagonal, metric.rs:42-54); reg = metric / temperature element-wise — the same f32 quotient the reference
@@ -158,29 +172,44 @@ __device__ __forceinline__ float sk_term(float p, float c) { return fmaxf(exp_c_
 // s + Σ_{i<8} term(pot[i], col[idx[i]·ld]) left to right; MASKED: only the first m (< 8) sources exist — the other
 // slots read stale scratch and contribute an exact +0.0
 template <bool MASKED>
-__device__ __forceinline__ float sk_rows8(float s, const float* __restrict__ col, const uint8_t* __restrict__ idx, const float* __restrict__ pot, int m) {
+__device__ __forceinline__ float sk_rows8(float s, const float* __restrict__ reg, unsigned col, const uint8_t* __restrict__ idx, const float* __restrict__ pot, int m) {
     const uint2 r8 = *reinterpret_cast<const uint2*>(idx);
     const float4 pa = *reinterpret_cast<const float4*>(pot), pb = *reinterpret_cast<const float4*>(pot + 4);
-    const float c0 = __ldg(col + (int)(r8.x & 0xFFu) * kSkLd), c1 = __ldg(col + (int)((r8.x >> 8) & 0xFFu) * kSkLd);
-    const float c2 = __ldg(col + (int)((r8.x >> 16) & 0xFFu) * kSkLd), c3 = __ldg(col + (int)(r8.x >> 24) * kSkLd);
-    const float c4 = __ldg(col + (int)(r8.y & 0xFFu) * kSkLd), c5 = __ldg(col + (int)((r8.y >> 8) & 0xFFu) * kSkLd);
-    const float c6 = __ldg(col + (int)((r8.y >> 16) & 0xFFu) * kSkLd), c7 = __ldg(col + (int)(r8.y >> 24) * kSkLd);
+    const float c0 = __ldg(reg + (col + ((unsigned)(r8.x & 0xFFu) << 8))), c1 = __ldg(reg + (col + ((unsigned)((r8.x >> 8) & 0xFFu) << 8)));
+    const float c2 = __ldg(reg + (col + ((unsigned)((r8.x >> 16) & 0xFFu) << 8))), c3 = __ldg(reg + (col + ((unsigned)(r8.x >> 24) << 8)));
+    const float c4 = __ldg(reg + (col + ((unsigned)(r8.y & 0xFFu) << 8))), c5 = __ldg(reg + (col + ((unsigned)((r8.y >> 8) & 0xFFu) << 8)));
+    const float c6 = __ldg(reg + (col + ((unsigned)((r8.y >> 16) & 0xFFu) << 8))), c7 = __ldg(reg + (col + ((unsigned)(r8.y >> 24) << 8)));
     float e0 = sk_term(pa.x, c0), e1 = sk_term(pa.y, c1), e2 = sk_term(pa.z, c2), e3 = sk_term(pa.w, c3);
     float e4 = sk_term(pb.x, c4), e5 = sk_term(pb.y, c5), e6 = sk_term(pb.z, c6), e7 = sk_term(pb.w, c7);
-    if (MASKED) {
-        e1 = m > 1 ? e1 : 0.0f; e2 = m > 2 ? e2 : 0.0f; e3 = m > 3 ? e3 : 0.0f; e4 = m > 4 ? e4 : 0.0f;
+    if (MASKED) {  // 5 <= m <= 7
         e5 = m > 5 ? e5 : 0.0f; e6 = m > 6 ? e6 : 0.0f; e7 = 0.0f;
     }
     s = s + e0; s = s + e1; s = s + e2; s = s + e3; s = s + e4; s = s + e5; s = s + e6; s = s + e7;
+    return s;
+}
+// the same for 1 <= m <= 4 sources
+__device__ __forceinline__ float sk_rows4(float s, const float* __restrict__ reg, unsigned col, const uint8_t* __restrict__ idx, const float* __restrict__ pot, int m) {
+    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx);
+    const float4 pa = *reinterpret_cast<const float4*>(pot);
+    const float c0 = __ldg(reg + (col + ((unsigned)r4.x << 8))), c1 = __ldg(reg + (col + ((unsigned)r4.y << 8)));
+    const float c2 = __ldg(reg + (col + ((unsigned)r4.z << 8))), c3 = __ldg(reg + (col + ((unsigned)r4.w << 8)));
+    const float e0 = sk_term(pa.x, c0);
+    float e1 = sk_term(pa.y, c1), e2 = sk_term(pa.z, c2), e3 = sk_term(pa.w, c3);
+    e1 = m > 1 ? e1 : 0.0f; e2 = m > 2 ? e2 : 0.0f; e3 = m > 3 ? e3 : 0.0f;
+    s = s + e0; s = s + e1; s = s + e2; s = s + e3;
     return s;
 }
 
 // One Gauss-Seidel half-sweep (sinkhorn.rs:96-129 `lhs()` / `rhs()` + `delta`): for every target t
 //   next_t = ln dens_t − ln Σ_s max(exp(pot_s − reg[t][s]), MIN_POSITIVE)      (Σ sequential over the source support)
 // replaces pot_t and returns Σ_t |exp(next_t) − exp(prev_t)| (sequential over the target support).
-__device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const float* __restrict__ lnd_t, const uint8_t* __restrict__ idx_t, int n_t,
-                                               const float* __restrict__ pot_s, const uint8_t* __restrict__ idx_s, int n_s,
-                                               float* __restrict__ tile, const float* __restrict__ reg, int lane) {
+__device__ __forceinline__ float sk_half_sweep(const SkSide tg, const SkSide sr, float* __restrict__ tile, const float* __restrict__ reg, int lane) {
+    float* __restrict__ pot_t = tg.pot;
+    const float* __restrict__ lnd_t = tg.lnd;
+    const uint8_t* __restrict__ idx_t = tg.idx;
+    const float* __restrict__ pot_s = sr.pot;
+    const uint8_t* __restrict__ idx_s = sr.idx;
+    const int n_t = tg.n, n_s = sr.n;
     float err = 0.0f;
     // issue-slot model: rows = ceil(n_t/32)·n_s exp steps; transposed = ceil4(n_t)·ceil(n_s/32) exp steps + the row adds
     const int n_t4 = (n_t + 3) & ~3;
@@ -188,35 +217,32 @@ __device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const 
     const int cost_tr = n_t4 * ((n_s + 31) >> 5) + (n_s >> 4) + 2;
     if (n_t <= kSkTrMax && cost_tr < cost_rows) {
         float s = 0.0f;  // lane t: running sum of target t
-        for (int s0 = 0; s0 < n_s; s0 += 64) {
-            const bool wide = n_s - s0 > 32;          // the slab's second half holds sources (warp-uniform)
-            const int sa = s0 + lane, sb = sa + 32;
-            const bool la = sa < n_s, lb = sb < n_s;
-            const float pa = la ? pot_s[sa] : 0.0f, pb = lb ? pot_s[sb] : 0.0f;
-            const float* __restrict__ cola = reg + (la ? (int)idx_s[sa] : 0);
-            const float* __restrict__ colb = reg + (lb ? (int)idx_s[sb] : 0);
+        for (int s0 = 0; s0 < n_s; s0 += 32) {
+            const int si = s0 + lane;
+            const bool live = si < n_s;
+            const float ps = live ? pot_s[si] : 0.0f;
+            const unsigned col = live ? (unsigned)idx_s[si] : 0u;
             // rows n_t..n_t4-1 of the tile are written from stale bucket ids (valid table rows) and never read
-            if (wide) {
-                for (int t = 0; t < n_t4; t += 4) {
-                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t + t);
-                    const int o0 = (int)r4.x * kSkLd, o1 = (int)r4.y * kSkLd, o2 = (int)r4.z * kSkLd, o3 = (int)r4.w * kSkLd;
-                    const float a0 = __ldg(cola + o0), a1 = __ldg(cola + o1), a2 = __ldg(cola + o2), a3 = __ldg(cola + o3);
-                    const float b0 = __ldg(colb + o0), b1 = __ldg(colb + o1), b2 = __ldg(colb + o2), b3 = __ldg(colb + o3);
-                    const float e0 = sk_term(pa, a0), e1 = sk_term(pa, a1), e2 = sk_term(pa, a2), e3 = sk_term(pa, a3);
-                    const float f0 = sk_term(pb, b0), f1 = sk_term(pb, b1), f2 = sk_term(pb, b2), f3 = sk_term(pb, b3);
-                    float* __restrict__ w = tile + t * kSkTile + lane;
-                    w[0] = la ? e0 : 0.0f; w[kSkTile] = la ? e1 : 0.0f; w[2 * kSkTile] = la ? e2 : 0.0f; w[3 * kSkTile] = la ? e3 : 0.0f;
-                    w[32] = lb ? f0 : 0.0f; w[kSkTile + 32] = lb ? f1 : 0.0f; w[2 * kSkTile + 32] = lb ? f2 : 0.0f; w[3 * kSkTile + 32] = lb ? f3 : 0.0f;
-                }
-            } else {
-                for (int t = 0; t < n_t4; t += 4) {
-                    const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t + t);
-                    const float a0 = __ldg(cola + (int)r4.x * kSkLd), a1 = __ldg(cola + (int)r4.y * kSkLd);
-                    const float a2 = __ldg(cola + (int)r4.z * kSkLd), a3 = __ldg(cola + (int)r4.w * kSkLd);
-                    const float e0 = sk_term(pa, a0), e1 = sk_term(pa, a1), e2 = sk_term(pa, a2), e3 = sk_term(pa, a3);
-                    float* __restrict__ w = tile + t * kSkTile + lane;
-                    w[0] = la ? e0 : 0.0f; w[kSkTile] = la ? e1 : 0.0f; w[2 * kSkTile] = la ? e2 : 0.0f; w[3 * kSkTile] = la ? e3 : 0.0f;
-                }
+            int t = 0;
+            for (; t + 8 <= n_t4; t += 8) {
+                const uint2 r8 = *reinterpret_cast<const uint2*>(idx_t + t);
+                const float c0 = __ldg(reg + (col + ((unsigned)(r8.x & 0xFFu) << 8))), c1 = __ldg(reg + (col + ((unsigned)((r8.x >> 8) & 0xFFu) << 8)));
+                const float c2 = __ldg(reg + (col + ((unsigned)((r8.x >> 16) & 0xFFu) << 8))), c3 = __ldg(reg + (col + ((unsigned)(r8.x >> 24) << 8)));
+                const float c4 = __ldg(reg + (col + ((unsigned)(r8.y & 0xFFu) << 8))), c5 = __ldg(reg + (col + ((unsigned)((r8.y >> 8) & 0xFFu) << 8)));
+                const float c6 = __ldg(reg + (col + ((unsigned)((r8.y >> 16) & 0xFFu) << 8))), c7 = __ldg(reg + (col + ((unsigned)(r8.y >> 24) << 8)));
+                const float e0 = sk_term(ps, c0), e1 = sk_term(ps, c1), e2 = sk_term(ps, c2), e3 = sk_term(ps, c3);
+                const float e4 = sk_term(ps, c4), e5 = sk_term(ps, c5), e6 = sk_term(ps, c6), e7 = sk_term(ps, c7);
+                float* __restrict__ w = tile + t * kSkTile + lane;
+                w[0] = live ? e0 : 0.0f; w[kSkTile] = live ? e1 : 0.0f; w[2 * kSkTile] = live ? e2 : 0.0f; w[3 * kSkTile] = live ? e3 : 0.0f;
+                w[4 * kSkTile] = live ? e4 : 0.0f; w[5 * kSkTile] = live ? e5 : 0.0f; w[6 * kSkTile] = live ? e6 : 0.0f; w[7 * kSkTile] = live ? e7 : 0.0f;
+            }
+            if (t < n_t4) {
+                const uchar4 r4 = *reinterpret_cast<const uchar4*>(idx_t + t);
+                const float c0 = __ldg(reg + (col + ((unsigned)r4.x << 8))), c1 = __ldg(reg + (col + ((unsigned)r4.y << 8)));
+                const float c2 = __ldg(reg + (col + ((unsigned)r4.z << 8))), c3 = __ldg(reg + (col + ((unsigned)r4.w << 8)));
+                const float e0 = sk_term(ps, c0), e1 = sk_term(ps, c1), e2 = sk_term(ps, c2), e3 = sk_term(ps, c3);
+                float* __restrict__ w = tile + t * kSkTile + lane;
+                w[0] = live ? e0 : 0.0f; w[kSkTile] = live ? e1 : 0.0f; w[2 * kSkTile] = live ? e2 : 0.0f; w[3 * kSkTile] = live ? e3 : 0.0f;
             }
             __syncwarp();
             if (lane < n_t) {  // dead sources hold +0.0: an exact no-op on a non-negative sum
@@ -225,13 +251,6 @@ __device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const 
                 for (int q = 0; q < 8; ++q) {
                     const float4 w = row[q];
                     s = s + w.x; s = s + w.y; s = s + w.z; s = s + w.w;
-                }
-                if (wide) {
-#pragma unroll
-                    for (int q = 8; q < 16; ++q) {
-                        const float4 w = row[q];
-                        s = s + w.x; s = s + w.y; s = s + w.z; s = s + w.w;
-                    }
                 }
             }
             __syncwarp();
@@ -245,14 +264,15 @@ __device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const 
         }
         err = ordered_sum32(err, v, tile, lane);
     } else {
-        const int n_s8 = n_s & ~7;
+        const int n_s8 = n_s & ~7, tail = n_s - n_s8;
         for (int t0 = 0; t0 < n_t; t0 += 32) {
             const int t = t0 + lane;
             const bool live = t < n_t;
-            const float* __restrict__ col = reg + (live ? (int)idx_t[t] : 0);
+            const unsigned col = live ? (unsigned)idx_t[t] : 0u;
             float s = 0.0f;
-            for (int q = 0; q < n_s8; q += 8) s = sk_rows8<false>(s, col, idx_s + q, pot_s + q, 8);
-            if (n_s8 < n_s) s = sk_rows8<true>(s, col, idx_s + n_s8, pot_s + n_s8, n_s - n_s8);
+            for (int q = 0; q < n_s8; q += 8) s = sk_rows8<false>(s, reg, col, idx_s + q, pot_s + q, 8);
+            if (tail > 4) s = sk_rows8<true>(s, reg, col, idx_s + n_s8, pot_s + n_s8, tail);
+            else if (tail > 0) s = sk_rows4(s, reg, col, idx_s + n_s8, pot_s + n_s8, tail);
             float v = 0.0f;
             if (live) {
                 const float prev = pot_t[t];
@@ -266,19 +286,20 @@ __device__ __forceinline__ float sk_half_sweep(float* __restrict__ pot_t, const 
     return err;
 }
 
-// OT cost of the problem currently loaded in `w` (both sides filled by sk_load_side); `metric` / `reg` are the dense
-// tables of sk_dense_tables.  `stats` (nullable): {solves, sweeps, exp terms} counters for the throughput reports.
-__device__ __forceinline__ float sk_solve(SkWarp& w, const float* __restrict__ metric, const float* __restrict__ reg, const SkParams hp, int lane,
+// OT cost of (mu, nu) — two sides of the warp scratch already filled with support and ln(density); `metric` / `reg`
+// are the dense tables of sk_dense_tables, `tile` the scratch's tile.  `stats` (nullable): {solves, sweeps, exp terms}.
+__device__ __forceinline__ float sk_solve(const SkSide mu, const SkSide nu, float* __restrict__ tile, const float* __restrict__ metric,
+                                          const float* __restrict__ reg, const SkParams hp, int lane,
                                           unsigned long long* __restrict__ stats = nullptr) {
-    const int nx = w.nx, ny = w.ny;
+    const int nx = mu.n, ny = nu.n;
     const float lx0 = ln_c(1.0f / (float)nx), ly0 = ln_c(1.0f / (float)ny);  // Phi::uniform (phi.rs:25-30)
-    for (int i = lane; i < nx; i += 32) w.lhs[i] = lx0;
-    for (int j = lane; j < ny; j += 32) w.rhs[j] = ly0;
+    for (int i = lane; i < nx; i += 32) mu.pot[i] = lx0;
+    for (int j = lane; j < ny; j += 32) nu.pot[j] = ly0;
     __syncwarp();
     int sweeps = 0;
     for (int t = 0; t < hp.iterations; ++t) {
-        const float lerr = sk_half_sweep(w.lhs, w.lnmu, w.ix, nx, w.rhs, w.iy, ny, w.tile, reg, lane);
-        const float rerr = sk_half_sweep(w.rhs, w.lnnu, w.iy, ny, w.lhs, w.ix, nx, w.tile, reg, lane);  // against the NEW lhs
+        const float lerr = sk_half_sweep(mu, nu, tile, reg, lane);
+        const float rerr = sk_half_sweep(nu, mu, tile, reg, lane);  // against the NEW lhs
         ++sweeps;
         if (lerr + rerr < hp.tolerance) break;
     }
@@ -290,16 +311,16 @@ __device__ __forceinline__ float sk_solve(SkWarp& w, const float* __restrict__ m
     // Coupling::cost: Σ_x Σ_y exp(lhs_x + rhs_y − reg)·C_xy, one accumulator, row-major
     float cost = 0.0f;
     for (int i = 0; i < nx; ++i) {
-        const int row = (int)w.ix[i] * kSkLd;
-        const float li = w.lhs[i];
+        const int row = (int)mu.idx[i] * kSkLd;
+        const float li = mu.pot[i];
         for (int j0 = 0; j0 < ny; j0 += 32) {
             const int j = j0 + lane;
             float v = 0.0f;
             if (j < ny) {
-                const int at = row + (int)w.iy[j];
-                v = exp_c(li + w.rhs[j] - __ldg(reg + at)) * __ldg(metric + at);
+                const int at = row + (int)nu.idx[j];
+                v = exp_c(li + nu.pot[j] - __ldg(reg + at)) * __ldg(metric + at);
             }
-            cost = ordered_sum32(cost, v, w.tile, lane);
+            cost = ordered_sum32(cost, v, tile, lane);
         }
     }
     return cost;
