@@ -35,14 +35,15 @@ def _worker(rank, world, port, batch, epochs, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_matches_single_process_emulation(tmp_path, oracle):
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_rank_gloo_matches_single_process_emulation(tmp_path, oracle, world):
     import torch.multiprocessing as mp
 
-    world, batch, epochs = 2, 96, 25
+    batch, epochs = 96, 25
     mp.spawn(_worker, args=(world, _free_port(), batch, epochs, str(tmp_path)), nprocs=world, join=True)
     rows = [np.load(tmp_path / f"rows{r}.npy") for r in range(world)]
-    assert rows[0].tobytes() == rows[1].tobytes()
-    # single-process emulation: two handles, concatenated partials, same fold
+    assert all(rows[0].tobytes() == r.tobytes() for r in rows[1:])
+    # single-process emulation: one handle per rank, concatenated partials, same fold
     r = [oracle.OracleSolver("leduc", "LinearRegret", "LinearWeight", "ExternalSampling", batch=batch, seed=21) for _ in range(world)]
     for k, s in enumerate(r):
         s.set_fold(1, k, world)
@@ -53,7 +54,7 @@ def test_two_rank_gloo_matches_single_process_emulation(tmp_path, oracle):
     assert r[0].profile_rows().tobytes() == rows[0].tobytes()
     # shards are disjoint and complete: per-rank counters add up to the whole epoch's work
     c = [np.load(tmp_path / f"counters{k}.npy") for k in range(world)]
-    assert c[0][0] + c[1][0] == r[0].counters()["nodes"] + r[1].counters()["nodes"]
+    assert sum(int(x[0]) for x in c) == sum(s.counters()["nodes"] for s in r)
     assert rows[0]["visits"].sum() > 0
 
 
@@ -148,15 +149,16 @@ def test_two_rank_gloo_nlhe_records_exchange(tmp_path, oracle):
     assert whole.export().tobytes() == rows[0].tobytes() and len(rows[0]) > 1000
 
 
-def test_two_rank_gloo_nlhe_owner_sharded_fold(tmp_path, oracle):
-    """Owner-sharded exchange (all-to-all of records to the infoset's owner, fold, all-gather of the touched rows): both
-    replicas end identical to ONE process running 2*batch trees."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_two_rank_gloo_nlhe_owner_sharded_fold(tmp_path, oracle, world):
+    """Owner-sharded exchange (all-to-all of records to the infoset's owner, fold, all-gather of the touched rows): every
+    replica ends identical to ONE process running world*batch trees."""
     import torch.multiprocessing as mp
 
-    world, batch, epochs = 2, 24, 3
+    batch, epochs = 24, 3
     mp.spawn(_nlhe_worker, args=(world, _free_port(), batch, epochs, str(tmp_path), "owner"), nprocs=world, join=True)
     rows = [np.load(tmp_path / f"nlhe{r}.npy") for r in range(world)]
-    assert rows[0].tobytes() == rows[1].tobytes()
+    assert all(rows[0].tobytes() == r.tobytes() for r in rows[1:])
     whole = oracle.OracleNlhe(seed=13, batch=world * batch)
     whole.step(epochs)
     assert whole.export().tobytes() == rows[0].tobytes() and len(rows[0]) > 1000

@@ -65,3 +65,42 @@ def test_flop_kmeans_bit_exact(rbp, oracle, n, k, bins, seed):
     oa2, od = o.lookup(with_distance=True)
     assert np.array_equal(a, oa2) and f32eq(d, od)       # bucket assignments, bit-exact
     assert f32eq(g.metric(), o.metric())
+
+
+@pytest.mark.parametrize("alpha,members", [(0.02, 40), (0.3, 12), (0.05, 3)])
+def test_mixture_points_against_merged_centroids_bit_exact(rbp, oracle, alpha, members):
+    # the shapes the flop layer meets: narrow points (both half-sweep schedules, 4/8-wide groups and
+    # masked tails) against centroids that are integer merges of member points
+    from lloyd_data import flop_mixture_histograms
+
+    bins = 256
+    tri = synthetic_metric(bins, 3)
+    pts = flop_mixture_histograms(48 * members, bins, comps=48, alpha=alpha, seed=7)
+    cen = pts.reshape(48, members, bins).astype(np.uint32).sum(axis=1)
+    rng = np.random.default_rng(11)
+    ia, ib = rng.integers(0, len(pts), 160), rng.integers(0, 48, 160)
+    a = pts.astype(np.uint32)
+    got_pc = rbp.lloyd.sinkhorn_divergence(a, cen, ia, ib, tri)          # distance(x, c)
+    got_cp = rbp.lloyd.sinkhorn_divergence(cen, a, ib, ia, tri)          # distance(c, x): not symmetric in f32
+    assert f32eq(got_pc, oracle.sinkhorn_divergence_batch(a[ia], cen[ib], tri, math=0, threads=8))
+    assert f32eq(got_cp, oracle.sinkhorn_divergence_batch(cen[ib], a[ia], tri, math=0, threads=8))
+
+
+def test_sinkhorn_counters_and_metric_validation(rbp):
+    from lloyd_data import flop_mixture_histograms
+
+    pts = flop_mixture_histograms(600, 64, comps=8, alpha=0.1, seed=2)
+    tri = synthetic_metric(64, 4)
+    g = rbp.lloyd.Layer(pts, 8, metric=tri)
+    g.init_centroids(0)
+    g.sinkhorn_stats(reset=True)
+    g.lookup()
+    solves, sweeps, terms = g.sinkhorn_stats(reset=True)
+    assert solves == 600 * 8 and solves <= sweeps <= 128 * solves and terms > sweeps    # one OT solve per (point, centroid)
+    assert g.sinkhorn_stats() == (0, 0, 0)
+    bad = tri.copy()
+    bad[5] = -0.25
+    with pytest.raises(rbp.RbpError):
+        rbp.lloyd.Layer(pts, 8, metric=bad)
+    with pytest.raises(rbp.RbpError):
+        rbp.lloyd.sinkhorn_divergence(pts[:2], pts[:2], [0], [1], bad)
