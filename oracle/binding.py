@@ -309,6 +309,13 @@ def ot_cost(mu, nu, tri, math=0, temperature=0.025, iterations=128, tolerance=0.
     return c, it.value
 
 
+def exp_c_min_over(lo, hi):
+    l = _sink()
+    l.orc_exp_c_min_over.restype = ctypes.c_float
+    l.orc_exp_c_min_over.argtypes = [ctypes.c_float, ctypes.c_float]
+    return l.orc_exp_c_min_over(lo, hi)
+
+
 def sinkhorn_divergence_batch(a, b, tri, math=0, threads=8):
     a = np.ascontiguousarray(a, dtype=np.uint32)
     b = np.ascontiguousarray(b, dtype=np.uint32)

@@ -8,6 +8,13 @@ using namespace orc;
 extern "C" {
 float orc_exp_c(float x) { return exp_c(x); }
 float orc_ln_c(float x) { return ln_c(x); }
+// min of exp_c over every float in [lo, hi] (both negative, lo <= hi): the GPU softmin drops the reference's
+// `.max(MIN_POSITIVE)` because the saturating contract never returns less — this is the exhaustive check of that claim
+float orc_exp_c_min_over(float lo, float hi) {
+    float m = INFINITY;
+    for (uint32_t u = bits_of(lo); u >= bits_of(hi); --u) { const float e = exp_c(f_from_bits(u)); if (!(e >= m)) m = e; }
+    return m;
+}
 // counts are dense u32[bins]; tri is the triangular ground metric; math: 0 contract, 1 libm
 float orc_ot_cost(const uint32_t* mu, const uint32_t* nu, int bins, const float* tri, int math, float temperature, int iterations,
                   float tolerance, int* iters_out) {

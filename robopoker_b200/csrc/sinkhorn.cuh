@@ -166,8 +166,11 @@ __device__ __forceinline__ float ordered_sum32(float acc, float v, float* buf, i
     return acc;
 }
 
-// softmin term max(exp(p − c), MIN_POSITIVE)  (sinkhorn.rs:118-120)
-__device__ __forceinline__ float sk_term(float p, float c) { return fmaxf(exp_c_le(p - c), kEps); }
+// softmin term max(exp(p − c), MIN_POSITIVE)  (sinkhorn.rs:118-120).  The saturating exp_c never returns less than
+// MIN_POSITIVE (its lower clamp is ln MIN_POSITIVE rounded up; checked exhaustively by
+// tests/test_oracle_sinkhorn.py::test_saturating_exp_never_returns_less_than_min_positive), so the max is the identity
+// and is not issued.
+__device__ __forceinline__ float sk_term(float p, float c) { return exp_c_le(p - c); }
 
 // s + Σ_{i<8} term(pot[i], col[idx[i]·ld]) left to right; MASKED: only the first m (< 8) sources exist — the other
 // slots read stale scratch and contribute an exact +0.0

@@ -41,6 +41,15 @@ def test_exp_ln_contract_close_to_libm(oracle):
     assert oracle.ln_c(1.0) == 0.0 and oracle.exp_c(0.0) == 1.0
 
 
+def test_saturating_exp_never_returns_less_than_min_positive(oracle):
+    # sinkhorn.rs:120 clamps every softmin term at MIN_POSITIVE; under the saturating contract the clamp is the identity
+    # (exhaustive over every float from the lower saturation point up to -80; above that exp(x) > 1e-35), which is why
+    # the device softmin (csrc/sinkhorn.cuh sk_term) has no max instruction
+    FLT_MIN = 1.17549435e-38
+    assert oracle.exp_c_min_over(-87.33654, -80.0) >= FLT_MIN
+    assert oracle.exp_c(-87.33654) >= FLT_MIN and oracle.exp_c(float("-inf")) >= FLT_MIN and oracle.exp_c(float("nan")) >= FLT_MIN
+
+
 def test_reference_property_tests_both_math_policies(oracle):
     tri = flop_metric()
     for m in (0, 1):
