@@ -32,6 +32,7 @@ def parse():
     p.add_argument("--batch", type=int, default=None, help="trees per epoch per GPU (default: 262144 leduc, 16384 nlhe)")
     p.add_argument("--table-slots", type=int, default=1 << 24, help="nlhe: infoset table capacity (power of two)")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--skip-cpu-baseline", action="store_true", help="tuning runs only: leave out the oracle's bounded CPU sample")
     p.add_argument("--fold", default="batched", choices=["ordered", "batched"],
                    help="ordered = reference Solver::step semantics (serial per row); batched = blocked delta sums (scales across GPUs)")
     a = p.parse_args()
@@ -248,15 +249,11 @@ def main_nlhe(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = None
     if phases is not None:
-        # dominant kernel: the value kernel.  Algorithmic bytes per launch: every preorder node read once (16 B) and one
-        # 72-byte update record written per walker node — the kernel re-reads nodes once per walker ancestor from L1/L2.
+        # dominant phase: the value kernels (child tasks of the large roots + small roots + combine).  Algorithmic bytes per
+        # epoch: every preorder node read once (16 B) and one 72-byte update record written per walker node — the scans
+        # re-read nodes once per walker ancestor from L1/L2.
         k_s = phases[2] * 1e-3 / args.steps
-        traffic = None
-        try:  # DRAM bytes per launch from the committed `ncu --set full` capture (taken at 16384 trees/epoch)
-            if args.batch == 16384:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["nlhe_value_kernel"]["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        traffic = None  # the committed ncu capture of this kernel (profiles/r1k_nlhe_value_ncu.txt) predates the split value phase
         alg = (16.0 * nodes + 72.0 * records * args.steps) / args.steps
         roofline = {"bound": "hbm", "kernel": "nlhe_value_kernel", "achieved": alg / k_s / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": alg / k_s / 1e9 / peak, "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
@@ -270,7 +267,7 @@ def main_nlhe(args):
                 "e2e": {"value": e_updates / e_dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64, "steps": e_steps,
                         "note": "no per-step host input exists on this path (device-side deals); the host reads the counter block every step"},
                 "gpu_launches": int(gpu_launches), "roofline": roofline, "epochs": c1["epochs"] + e_steps, "table_rows": s.counters()["rows"]}
-        if world == 1:
+        if world == 1 and not args.skip_cpu_baseline:
             from oracle import binding as oracle
 
             threads = os.cpu_count() or 1
