@@ -2,7 +2,7 @@
 """Secondary benchmark (BASELINE.json configs[4], turn+river EMD k-means sweep): seconds/iteration, distance
 evaluations/s and achieved GB/s of the Elkan step vs the HBM roofline, next to the oracle on the host cores.
 
-    python tools/bench_lloyd.py --n 1000000 --k 100 256 500 2000 --iters 4
+    python tests/measure/bench_lloyd.py --n 1000000 --k 100 256 500 2000 --iters 4
 """
 import argparse
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

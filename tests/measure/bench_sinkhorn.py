@@ -3,7 +3,7 @@
 Elkan step on synthetic flop histograms (47 draws from a Dirichlet mixture over 256 turn clusters) against K centroids,
 reported as OT solves/s and exp terms/s against the FP32-issue ceiling, next to the oracle on the host cores.
 
-    python tools/bench_sinkhorn.py --n 20000 --k 200
+    python tests/measure/bench_sinkhorn.py --n 20000 --k 200
 """
 import argparse
 import ctypes
@@ -12,7 +12,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -7,7 +7,7 @@ power-of-two epoch.  One JSON line per (batch, checkpoint): both exploitabilitie
 the wall-clock of each side up to that checkpoint.  batch=1 x 2^20 epochs is the reference-faithful run
 (`batch_size() == 1`, crates/leduc/src/solver.rs); larger batches are the throughput configurations.
 
-    python tools/leduc_curve.py --trees 1048576 --batch 1 1024 16384
+    python tests/measure/leduc_curve.py --trees 1048576 --batch 1 1024 16384
 """
 import argparse
 import json
@@ -15,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -11,8 +11,8 @@ import json,sys
 d=json.load(open(sys.argv[1])); print(sys.argv[1], "%.4g updates/s" % d["value"], "%.3f ms/step" % d["ms_per_step"], d["roofline"]["kernel_ms"], "launches", d["gpu_launches"])
 PY
 done
-timeout 200 python tools/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0 --tag a02_w8b3 > $O/sk_${TAG}_a02_w8b3.json 2>> $O/bench_${TAG}.err
-timeout 300 python tools/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1 --tag a30_w8b3 > $O/sk_${TAG}_a30_w8b3.json 2>> $O/bench_${TAG}.err
+timeout 200 python tests/measure/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0 --tag a02_w8b3 > $O/sk_${TAG}_a02_w8b3.json 2>> $O/bench_${TAG}.err
+timeout 300 python tests/measure/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1 --tag a30_w8b3 > $O/sk_${TAG}_a30_w8b3.json 2>> $O/bench_${TAG}.err
 for f in $O/sk_${TAG}_*.json; do python - "$f" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))

@@ -4,18 +4,18 @@ O=gpurun_out
 TAG=${1:-r1n}
 mkdir -p $O
 timeout 600 python -m pytest tests/test_sinkhorn_gpu.py -x -q --timeout 300 > $O/pytest_sk_${TAG}.log 2>&1; tail -3 $O/pytest_sk_${TAG}.log
-B="python tools/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0"
+B="python tests/measure/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0"
 timeout 300 $B --tag a02_w8b3 --cpu-pairs 2048 > $O/sk_${TAG}_a02_w8b3.json 2> $O/sk_${TAG}.err
 RBP_SK_WARPS=8 RBP_SK_BLOCKS_PER_SM=2 timeout 200 $B --tag a02_w8b2 > $O/sk_${TAG}_a02_w8b2.json 2>> $O/sk_${TAG}.err
 RBP_SK_WARPS=4 RBP_SK_BLOCKS_PER_SM=6 timeout 200 $B --tag a02_w4b6 > $O/sk_${TAG}_a02_w4b6.json 2>> $O/sk_${TAG}.err
 RBP_SK_WARPS=8 RBP_SK_BLOCKS_PER_SM=1 timeout 200 $B --tag a02_w8b1 > $O/sk_${TAG}_a02_w8b1.json 2>> $O/sk_${TAG}.err
 RBP_LIB_PATH=$PWD/tools/_prev/librbp_b200_prev.so timeout 300 $B --tag a02_prev --sweeps 1 > $O/sk_${TAG}_a02_prev.json 2>> $O/sk_${TAG}.err
-B3="python tools/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1"
+B3="python tests/measure/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1"
 timeout 300 $B3 --tag a30_w8b3 > $O/sk_${TAG}_a30_w8b3.json 2>> $O/sk_${TAG}.err
 RBP_SK_WARPS=8 RBP_SK_BLOCKS_PER_SM=2 timeout 300 $B3 --tag a30_w8b2 > $O/sk_${TAG}_a30_w8b2.json 2>> $O/sk_${TAG}.err
 RBP_LIB_PATH=$PWD/tools/_prev/librbp_b200_prev.so timeout 300 $B3 --tag a30_prev > $O/sk_${TAG}_a30_prev.json 2>> $O/sk_${TAG}.err
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sk_assign_kernel --launch-skip 1 -c 1 -o $O/${TAG}_sk_assign -f \
-  python tools/bench_sinkhorn.py --n 3000 --k 64 --cpu-pairs 0 --sweeps 1 --steps 1 > $O/ncu_sk_${TAG}.log 2>&1
+  python tests/measure/bench_sinkhorn.py --n 3000 --k 64 --cpu-pairs 0 --sweeps 1 --steps 1 > $O/ncu_sk_${TAG}.log 2>&1
 for f in $O/sk_${TAG}_*.json; do python - "$f" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))

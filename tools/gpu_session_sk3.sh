@@ -4,16 +4,16 @@ O=gpurun_out
 TAG=${1:-r1o}
 mkdir -p $O
 timeout 600 python -m pytest tests/test_sinkhorn_gpu.py -x -q --timeout 300 > $O/pytest_sk_${TAG}.log 2>&1; tail -3 $O/pytest_sk_${TAG}.log
-B="python tools/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0"
+B="python tests/measure/bench_sinkhorn.py --n 16000 --k 200 --cpu-pairs 0"
 for shape in "8 3" "8 4" "8 2" "4 6" "4 8"; do set -- $shape
   RBP_SK_WARPS=$1 RBP_SK_BLOCKS_PER_SM=$2 timeout 200 $B --tag a02_w$1b$2 > $O/sk_${TAG}_a02_w$1b$2.json 2>> $O/sk_${TAG}.err
 done
-B3="python tools/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1"
+B3="python tests/measure/bench_sinkhorn.py --n 4000 --k 200 --alpha 0.3 --cpu-pairs 0 --sweeps 1"
 for shape in "8 3" "8 4"; do set -- $shape
   RBP_SK_WARPS=$1 RBP_SK_BLOCKS_PER_SM=$2 timeout 300 $B3 --tag a30_w$1b$2 > $O/sk_${TAG}_a30_w$1b$2.json 2>> $O/sk_${TAG}.err
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sk_assign_kernel --launch-skip 1 -c 1 -o $O/${TAG}_sk_assign -f \
-  python tools/bench_sinkhorn.py --n 3000 --k 64 --cpu-pairs 0 --sweeps 1 --steps 1 > $O/ncu_sk_${TAG}.log 2>&1
+  python tests/measure/bench_sinkhorn.py --n 3000 --k 64 --cpu-pairs 0 --sweeps 1 --steps 1 > $O/ncu_sk_${TAG}.log 2>&1
 for f in $O/sk_${TAG}_*.json; do python - "$f" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))
