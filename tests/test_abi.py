@@ -56,3 +56,29 @@ def test_no_cpu_fallback(rbp):
     with pytest.raises(rbp.RbpError) as e:
         rbp.Solver("kuhn")
     assert e.value.status == -2  # RBP_ERR_NO_DEVICE
+
+
+def test_every_compute_family_refuses_without_a_device(rbp):
+    """NLHE solver, both k-means layers, batched Sinkhorn, hand evaluation, river equity, isomorphism sets: each entry
+    point reports RBP_ERR_NO_DEVICE on a CPU-only host instead of computing anything."""
+    import numpy as np
+
+    if rbp.load_library().rbp_device_count() > 0:
+        pytest.skip("GPU present")
+    from robopoker_b200.nlhe import Nlhe
+
+    turn = np.zeros((4, 101), np.uint8); turn[:, 50] = 46
+    flop = np.zeros((4, 32), np.uint8); flop[:, 3] = 47
+    tri = np.full(32 * 31 // 2, 0.5, np.float32)
+    hands = np.array([0x7F], np.uint64)
+    calls = [lambda: Nlhe(batch=8, seed=0, table_slots=1 << 10),
+             lambda: rbp.lloyd.Layer(turn, 2),
+             lambda: rbp.lloyd.Layer(flop, 2, metric=tri),
+             lambda: rbp.lloyd.sinkhorn_divergence(flop, flop, [0], [1], tri),
+             lambda: rbp.deuce.strength(hands),
+             lambda: rbp.deuce.river_equity(np.array([0x3], np.uint64), np.array([0x7C], np.uint64)),
+             lambda: rbp.deuce.IsoSet("flop")]
+    for call in calls:
+        with pytest.raises(rbp.RbpError) as e:
+            call()
+        assert e.value.status == -2, call
