@@ -67,6 +67,20 @@ def test_profile_parity(rbp, oracle, regret, weight, sampling, batch, epochs, wa
     trees_equal(g, o, range(0, batch, max(1, batch // 7)))  # trees of the next epoch read the trained table
 
 
+def test_profile_parity_with_the_large_epoch_walker_sort(rbp, oracle, monkeypatch):
+    # epochs whose preorder arrays exceed L2 break size ties of the walker sort by tree index (32-bit keys); that path is
+    # forced here at a size the oracle can follow, together with a split threshold that sends most roots through the
+    # per-child tasks
+    monkeypatch.setenv("RBP_NLHE_TIEBREAK", "1")
+    monkeypatch.setenv("RBP_NLHE_SPLIT", "24")
+    g, o = make(rbp, oracle, 160, 31)
+    g.step(5), o.step(5)
+    rows_equal(g.profile(), o.export())
+    cg, co = g.counters(), o.counters()
+    for k in ("epochs", "nodes", "infos", "updates", "rows"):
+        assert cg[k] == co[k], (k, cg, co)
+
+
 def test_export_import_roundtrip(rbp, oracle):
     g, o = make(rbp, oracle, 64, 3)
     g.step(3), o.step(5)
