@@ -56,22 +56,51 @@ def test_kuhn_nash_equilibrium(oracle):
     assert s.exploitability() < 0.020
 
 
-# crates/kuhn/src/solver.rs:234-277 — a representative slice of the 44-combo matrix (same thresholds)
-KUHN_COMBOS = [
-    ("ExternalSampling", "SummedRegret", "ConstantWeight", 0.020),
-    ("ExternalSampling", "LinearRegret", "LinearWeight", 0.020),
-    ("ExternalSampling", "FlooredRegret", "QuadraticWeight", 0.020),
-    ("ExternalSampling", "AsymmetricRegret", "ExponentialWeight", 0.030),
-    ("ExternalSampling", "DiscountedRegret", "LinearWeight", 0.020),
-    ("PrunableSampling", "FlooredRegret", "LinearWeight", 0.020),
-    ("PluribusSampling", "DiscountedRegret", "ConstantWeight", 0.020),
-]
+# crates/kuhn/src/solver.rs:234-277 and crates/roshambo/src/solver.rs:205-250: the reference's full 44-combination test
+# matrices (sampling x regret x weight, same iteration counts, same tolerances), transcribed into
+# tests/golden/solver_combos.json by tests/golden/make_solver_combos.py
+def _combos(key):
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_combos.json")))[key]
 
 
-@pytest.mark.parametrize("sampling,regret,weight,tol", KUHN_COMBOS)
-def test_kuhn_exploitability_thresholds(oracle, sampling, regret, weight, tol):
-    s = oracle.OracleSolver("kuhn", regret, weight, sampling).solve(N18)
-    assert s.exploitability() < tol
+def _run_all(jobs):
+    from concurrent.futures import ThreadPoolExecutor  # the oracle runs outside the GIL
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        return [f for f in pool.map(lambda job: job(), jobs) if f]
+
+
+def test_kuhn_exploitability_thresholds_all_44(oracle):
+    combos = _combos("kuhn_exploitability_after_2^18")
+    assert len(combos) == 44
+
+    def job(c):
+        def run():
+            e = oracle.OracleSolver("kuhn", c["regret"], c["weight"], c["sampling"]).solve(N18).exploitability()
+            return None if e < c["tolerance"] else (c, e)
+        return run
+
+    assert _run_all([job(c) for c in combos]) == []
+
+
+def test_rps_equilibrium_all_44(oracle):
+    combos = _combos("rps_equilibrium_after_2^16")
+    assert len(combos) == 44
+
+    def job(c):
+        def run():
+            s = oracle.OracleSolver("rps", c["regret"], c["weight"], c["sampling"]).solve(1 << 16)
+            for key in (1, 3):  # P1, P2
+                r, p, sc = s.averaged_distribution(key)
+                if not (abs(r - 0.40) < c["tolerance"] and abs(p - 0.40) < c["tolerance"] and abs(sc - 0.20) < c["tolerance"]):
+                    return (c, key, r, p, sc)
+            return None
+        return run
+
+    assert _run_all([job(c) for c in combos]) == []
 
 
 # crates/leduc/src/solver.rs:121-123
