@@ -53,9 +53,9 @@ typedef struct {
 
 /* generic choices R, W, S of `trait Solver` (crates/mccfr/src/solver/solver.rs:38-74) as enums */
 enum { RBP_GAME_KUHN = 0, RBP_GAME_LEDUC = 1, RBP_GAME_RPS = 2 /* crates/roshambo: info_key = bit0 acting | bits1-2 player */ };
-enum { RBP_REGRET_SUMMED = 0, RBP_REGRET_FLOORED = 1, RBP_REGRET_LINEAR = 2, RBP_REGRET_DISCOUNTED = 3, RBP_REGRET_ASYMMETRIC = 4 }; /* crates/mccfr/src/regret/*.rs */
-enum { RBP_WEIGHT_CONSTANT = 0, RBP_WEIGHT_LINEAR = 1, RBP_WEIGHT_QUADRATIC = 2, RBP_WEIGHT_EXPONENTIAL = 3 };                       /* crates/mccfr/src/policy/*.rs */
-enum { RBP_SAMPLING_EXTERNAL = 0, RBP_SAMPLING_VANILLA = 1, RBP_SAMPLING_PRUNABLE = 2, RBP_SAMPLING_PLURIBUS = 3, RBP_SAMPLING_TARGETED = 4 };                  /* crates/mccfr/src/sample/*.rs */
+enum { RBP_REGRET_SUMMED = 0, RBP_REGRET_FLOORED = 1, RBP_REGRET_LINEAR = 2, RBP_REGRET_DISCOUNTED = 3, RBP_REGRET_ASYMMETRIC = 4 }; /* crates/mccfr/src/regret/ (every schedule file) */
+enum { RBP_WEIGHT_CONSTANT = 0, RBP_WEIGHT_LINEAR = 1, RBP_WEIGHT_QUADRATIC = 2, RBP_WEIGHT_EXPONENTIAL = 3 };                       /* crates/mccfr/src/policy/ (every schedule file) */
+enum { RBP_SAMPLING_EXTERNAL = 0, RBP_SAMPLING_VANILLA = 1, RBP_SAMPLING_PRUNABLE = 2, RBP_SAMPLING_PLURIBUS = 3, RBP_SAMPLING_TARGETED = 4 };                  /* crates/mccfr/src/sample/ (every scheme file) */
 /* how the per-tree Decisions of one epoch are folded into the table:
  *   ORDERED — reference semantics (solver.rs:96-105): one schedule application per Decisions, in tree order.
  *   BATCHED — one schedule application per row per epoch on the blocked-order sum of the deltas
