@@ -37,3 +37,15 @@ def test_cpp_mirror_refuses_without_a_device(rbp, tmp_path):
 @pytest.mark.gpu
 def test_cpp_mirror_drives_the_library(rbp, tmp_path):
     assert "device: 0 failures" in _run(_build(tmp_path))
+
+
+def test_header_is_a_plain_c_abi(rbp, tmp_path):
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "abi_plain_c")
+    lib_dir = os.path.join(ROOT, "robopoker_b200")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_plain_c.c"), "-o", exe, "-L", lib_dir, "-l:librbp_b200.so", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    _run(exe)
