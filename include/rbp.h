@@ -166,7 +166,8 @@ int rbp_nlhe_counters(rbp_nlhe_t* s, uint64_t out[8]);
 typedef struct {
     int64_t past;    /* i64::from(info.subgame()) — Path, 5 bits per edge, first edge lowest (crates/kicker/src/path.rs) */
     int64_t choices; /* i64::from(info.choices()) */
-    int64_t edge;    /* u8 code of the edge (crates/kicker/src/edge.rs:117-135) */
+    int64_t edge;    /* u64::from(Edge) as i64 (crates/kicker/src/edge.rs:185-197): Draw 0, Fold 1, Check 2, Call 3, Raise 4 | numer << 3 | denom << 11,
+                      * Shove 5, Open 6 | n << 3.  Import also reads the legacy BBs form (tag 4, bit 19; edge.rs:168-172).  NOT the 5-bit path code. */
     int16_t present; /* i16::from(info.bucket()) — Abstraction */
     int16_t pad[3];
     rbp_encounter_t row;

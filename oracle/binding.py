@@ -407,6 +407,16 @@ def nlhe_edge(name, *args):
     return NLHE_EDGES[name]
 
 
+def nlhe_edge_u64(code):
+    """5-bit path code → `u64::from(Edge)` (kicker/src/edge.rs:185-197), the blueprint table's `edge` column."""
+    return int(_nlhe().orc_nlhe_edge_u64(int(code)))
+
+
+def nlhe_edge_from_u64(value):
+    """`Edge::from(u64)` (kicker/src/edge.rs:160-183, legacy BBs form included) → 5-bit path code (0 = not on the grid)."""
+    return int(_nlhe().orc_nlhe_edge_from_u64(int(value)))
+
+
 def nlhe_path(edges):
     p = 0
     for i, e in enumerate(edges[:12]):
@@ -433,6 +443,10 @@ def _nlhe():
         l.orc_nlhe_path_push.argtypes = [u64, i32]
         l.orc_nlhe_raises.argtypes = [i32, i32, vp]
         l.orc_nlhe_into_chips.argtypes = [i32, i32]
+        l.orc_nlhe_edge_u64.restype = u64
+        l.orc_nlhe_edge_u64.argtypes = [i32]
+        l.orc_nlhe_edge_from_u64.restype = i32
+        l.orc_nlhe_edge_from_u64.argtypes = [u64]
         l.orc_nlhe_default_regret.restype = ctypes.c_float
         l.orc_nlhe_default_regret.argtypes = [i32]
         l.orc_nlhe_deck_draw.argtypes = [ctypes.POINTER(u64), u32]

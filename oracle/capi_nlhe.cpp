@@ -111,6 +111,8 @@ int orc_nlhe_aggression(uint64_t path) { return path_aggression(path); }
 uint64_t orc_nlhe_path_push(uint64_t path, int edge) { return path_push(path, (uint8_t)edge); }
 int orc_nlhe_raises(int street, int depth, uint8_t* out) { return raises(street, depth, out); }
 int orc_nlhe_into_chips(int edge, int pot) { return into_chips((uint8_t)edge, (Chips)pot); }
+uint64_t orc_nlhe_edge_u64(int edge) { return e_to_u64((uint8_t)edge); }
+int orc_nlhe_edge_from_u64(uint64_t v) { return e_from_u64(v); }
 float orc_nlhe_default_regret(int edge) { return e_default_regret((uint8_t)edge); }
 int orc_nlhe_deck_draw(uint64_t* deck, uint32_t word) { return deck_draw(deck, word); }
 uint16_t orc_nlhe_abstraction(uint64_t pocket, uint64_t board) {
@@ -192,7 +194,7 @@ uint64_t orc_nlhe_export(nlhe::Solver* s, OrcNlheRow* out, uint64_t cap) {
             if (!p->second.present[a]) continue;
             if (out && k < cap) {
                 const Encounter& e = p->second.e[a];
-                out[k] = OrcNlheRow{(int64_t)p->first.subgame, (int64_t)p->first.choices, (int64_t)p->second.edges[a], (int16_t)p->first.abs, {0, 0, 0},
+                out[k] = OrcNlheRow{(int64_t)p->first.subgame, (int64_t)p->first.choices, (int64_t)e_to_u64(p->second.edges[a]), (int16_t)p->first.abs, {0, 0, 0},
                                     e.weight, e.regret, e.payoff, (int32_t)e.visits};
             }
             ++k;

@@ -73,6 +73,31 @@ inline Chips into_chips(uint8_t e, Chips pot) {  // edge.rs:89-95
     if (e >= E_OPEN0) return (Chips)(kOpens[e - E_OPEN0] * kBB);
     return 0;
 }
+// edge.rs:185-197 `impl From<Edge> for u64` — the blueprint table's `edge` column (nlhe/src/profile.rs:143-160), NOT the 5-bit
+// path code: Draw 0, Fold 1, Check 2, Call 3, Raise(n/d) 4 | n << 3 | d << 11, Shove 5, Open(n) 6 | n << 3
+inline uint64_t e_to_u64(uint8_t e) {
+    if (e >= E_RAISE0) return 4u | (uint64_t)kRaises[e - E_RAISE0][0] << 3 | (uint64_t)kRaises[e - E_RAISE0][1] << 11;
+    if (e >= E_OPEN0) return 6u | (uint64_t)kOpens[e - E_OPEN0] << 3;
+    return e == E_SHOVE ? 5u : (uint64_t)(e - 1);
+}
+// edge.rs:160-183 `impl From<u64> for Edge` incl. the legacy form (tag 4 with bit 19 = BBs, read as Open); 0 = not on this grid
+inline uint8_t e_from_u64(uint64_t v) {
+    const uint64_t lo = v >> 3 & 0xFF, hi = v >> 11 & 0xFF;
+    auto open = [&](uint64_t n) -> uint8_t { for (int i = 0; i < 4; ++i) if ((uint64_t)kOpens[i] == n) return (uint8_t)(E_OPEN0 + i); return 0; };
+    switch (v & 0b111) {
+        case 0: return E_DRAW;
+        case 1: return E_FOLD;
+        case 2: return E_CHECK;
+        case 3: return E_CALL;
+        case 5: return E_SHOVE;
+        case 6: return open(lo);
+        case 4:
+            if (v & (1ull << 19)) return open(lo);
+            for (int i = 0; i < 10; ++i) if ((uint64_t)kRaises[i][0] == lo && (uint64_t)kRaises[i][1] == hi) return (uint8_t)(E_RAISE0 + i);
+            return 0;
+        default: return 0;
+    }
+}
 
 // path.rs: 5 bits per edge, first edge in the low bits, at most 12 edges
 inline uint64_t path_push(uint64_t p, uint8_t e) {

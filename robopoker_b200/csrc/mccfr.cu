@@ -821,6 +821,7 @@ struct rbp_solver {
     bool own_stream = true;
     int device = 0, regret = 0, weight = 0, sampling = 0, fold_mode = 0, batch = 1;
     int world_rank = 0, world_size = 1;
+    bool sampled = false;  // rbp_solver_sample ran for the current epoch (its partial sums are what fold_gathered consumes)
     uint64_t seed = 0, epochs = 0;
     rbp_hyper_t hyper{};
     size_t sample_smem = 0, fold_smem = 0;
@@ -1242,6 +1243,7 @@ int rbp_solver_sample(rbp_solver_t* s) {
     if ((st = launch_sample(s, ep))) return st;
     if ((st = launch_rank_partial(s))) return st;
     RBP_CUDA(cudaStreamSynchronize(s->stream));
+    s->sampled = true;
     return RBP_OK;
 }
 int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes) {
@@ -1254,10 +1256,13 @@ int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes) {
 int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size) {
     if (!s || !dev_gathered || world_size < 1) return RBP_ERR_INVALID;
     if (s->fold_mode != RBP_FOLD_BATCHED) return RBP_ERR_STATE;
+    if (world_size != s->world_size) { set_last_error("rbp_solver_fold_gathered: world_size differs from rbp_solver_set_world"); return RBP_ERR_INVALID; }
+    if (!s->sampled) { set_last_error("rbp_solver_fold_gathered before rbp_solver_sample"); return RBP_ERR_STATE; }
     RBP_CUDA(cudaSetDevice(s->device));
     EpochArgs ep = epoch_args(s);
     int st;
     if ((st = launch_apply_batched(s, ep, static_cast<const Partial*>(dev_gathered), world_size))) return st;
+    s->sampled = false;
     s->epochs += 1;
     RBP_CUDA(cudaStreamSynchronize(s->stream));
     return RBP_OK;

@@ -13,7 +13,10 @@ from .solver import REGRETS, SAMPLERS, WEIGHTS
 ROW_DTYPE = np.dtype([("past", "<i8"), ("choices", "<i8"), ("edge", "<i8"), ("present", "<i2"), ("pad", "<i2", 3),
                       ("weight", "<f4"), ("regret", "<f4"), ("payoff", "<f4"), ("visits", "<u4")])
 NODE_DTYPE = np.dtype([("depth", "u1"), ("kind", "u1"), ("act", "u1"), ("pad", "u1"), ("p", "<f4"), ("q", "<f4"), ("payoff", "<f4")])
-EDGES = {"Draw": 1, "Fold": 2, "Check": 3, "Call": 4, "Shove": 5}  # kicker/src/edge.rs:117-135; Open(n) 6.., Raise(odds) 10..
+# 5-bit codes inside `past` / `choices` Paths (kicker/src/edge.rs:117-135; Open(n) 6.., Raise(odds) 10..) ...
+EDGES = {"Draw": 1, "Fold": 2, "Check": 3, "Call": 4, "Shove": 5}
+# ... and the `edge` COLUMN of a blueprint row, which is `u64::from(Edge)` (kicker/src/edge.rs:185-197):
+EDGE_COLUMN = {"Draw": 0, "Fold": 1, "Check": 2, "Call": 3, "Shove": 5}  # Raise(n/d) = 4 | n << 3 | d << 11, Open(n) = 6 | n << 3
 
 
 class Nlhe:

@@ -93,6 +93,31 @@ def test_export_import_roundtrip(rbp, oracle):
     rows_equal(h.profile(), o.export())
 
 
+def test_blueprint_edge_column_is_the_reference_u64(rbp, oracle):
+    """`rbp_nlhe_export` writes `u64::from(Edge)` (kicker/src/edge.rs:185-197) in the edge column and `rbp_nlhe_import` reads it,
+    including the legacy BBs form and rows in the reference's (unsorted, HashMap) order; foreign edges are rejected."""
+    from robopoker_b200.nlhe import Nlhe
+    g = Nlhe(batch=64, seed=3, table_slots=1 << 17)
+    g.step(2)
+    rows = g.profile()
+    legal = {0, 1, 2, 3, 5, 22, 30, 38, 46, 8204, 6156, 4108, 6164, 8220, 2060, 8236, 4124, 2068, 2076}  # written out from edge.rs / pokerkit RAISES, OPENS
+    assert set(int(v) for v in np.unique(rows["edge"])) <= legal and 1 in rows["edge"] and 5 in rows["edge"]
+    for row in rows[:300]:
+        assert oracle.nlhe_edge_from_u64(int(row["edge"])) in oracle.nlhe_unpath(int(row["choices"]))
+    legacy = rows.copy()
+    opens = (legacy["edge"] & 7) == 6
+    assert opens.any()
+    legacy["edge"][opens] = 4 | (legacy["edge"][opens] >> 3 & 0xFF) << 3 | 1 << 19   # old Size::BBs encoding (edge.rs:168-172)
+    legacy = legacy[np.random.default_rng(0).permutation(len(legacy))]
+    h = Nlhe(batch=64, seed=3, table_slots=1 << 17)
+    h.load(legacy, 2)
+    assert h.profile().tobytes() == rows.tobytes()
+    bad = rows[:4].copy()
+    bad["edge"][0] = 4 | 7 << 3 | 9 << 11  # Raise(7/9) is not on the Pluribus grid
+    with pytest.raises(rbp.RbpError):
+        h.load(bad, 2)
+
+
 def test_capacity_errors_are_loud(rbp):
     from robopoker_b200.nlhe import Nlhe
     g = Nlhe(batch=256, seed=1, table_slots=1 << 10)

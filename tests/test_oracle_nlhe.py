@@ -142,6 +142,29 @@ def test_root_choices(oracle):  # kicker game.rs choices(): raises, shove, call,
     assert oracle.nlhe_unpath(int(p[3]["choices"])) == [10, 12, 14, 15, 18, 5, 3]
 
 
+def test_blueprint_edge_column_is_u64_from_edge(oracle):
+    """The blueprint row stores `u64::from(Edge)` (nlhe/src/profile.rs:143-160), whose layout is kicker/src/edge.rs:185-197:
+    Draw 0, Fold 1, Check 2, Call 3, Raise 4 | numer << 3 | denom << 11, Shove 5, Open 6 | n << 3 — values written out by hand
+    from that file, not computed by the code under test."""
+    e = oracle.nlhe_edge
+    golden = {e("Draw"): 0, e("Fold"): 1, e("Check"): 2, e("Call"): 3, e("Shove"): 5,
+              e("Open", 2): 22, e("Open", 3): 30, e("Open", 4): 38, e("Open", 5): 46,
+              e("Raise", 1, 4): 8204, e("Raise", 1, 3): 6156, e("Raise", 1, 2): 4108, e("Raise", 2, 3): 6164, e("Raise", 3, 4): 8220,
+              e("Raise", 1, 1): 2060, e("Raise", 5, 4): 8236, e("Raise", 3, 2): 4124, e("Raise", 2, 1): 2068, e("Raise", 3, 1): 2076}
+    assert len(golden) == 19
+    for code, value in golden.items():
+        assert oracle.nlhe_edge_u64(code) == value
+        assert oracle.nlhe_edge_from_u64(value) == code
+    # `From<u64> for Edge` keeps the old Size encoding readable: tag 4 with bit 19 set = BBs(n) → Open(n) (edge.rs:168-172)
+    assert oracle.nlhe_edge_from_u64(4 | 3 << 3 | 1 << 19) == e("Open", 3)
+    # not on the grid (the reference would build an Edge our tree never produces): rejected, not aliased
+    assert oracle.nlhe_edge_from_u64(4 | 7 << 3 | 9 << 11) == 0 and oracle.nlhe_edge_from_u64(7) == 0
+    o = oracle.OracleNlhe(seed=3, batch=8)
+    o.step(1)
+    rows = o.export()
+    assert set(int(v) for v in np.unique(rows["edge"])) <= set(golden.values())
+
+
 def test_edge_replay_subgame_and_snap(oracle):  # nlhe/src/game.rs apply + info.rs: subgame = this street's choice edges
     e = oracle.nlhe_edge
     path = [e("Open", 3), e("Raise", 1, 1), e("Call"), e("Draw"), e("Check"), e("Raise", 1, 2), e("Call"), e("Draw")]
@@ -199,7 +222,7 @@ def test_solver_thread_invariance_and_shape(oracle):
     assert c["epochs"] == 3 and c["updates"] > 0 and c["nodes"] > 32 * 3 * 10
     assert set(np.unique(ra["present"] >> 8)) <= {0, 1, 2, 3}
     for row in ra[:200]:  # every stored edge is one of its infoset's choices; walker rows hold every choice after one visit
-        assert int(row["edge"]) in oracle.nlhe_unpath(int(row["choices"]))
+        assert oracle.nlhe_edge_from_u64(int(row["edge"])) in oracle.nlhe_unpath(int(row["choices"]))
     assert np.all(ra["visits"] >= 1) and np.all(np.isfinite(ra["regret"])) and np.all(ra["weight"] >= 0)
     d = oracle.OracleNlhe(seed=10, batch=32, threads=1)
     d.step(3)
