@@ -29,6 +29,23 @@ const char* rbp_last_error(void);
 uint64_t rbp_kernel_launches(void);
 int rbp_device_count(void);
 
+/* ─────────────────────────────── multi-GPU: one process per GPU ─────────────────────────────── */
+
+/* The reference's fast path is one rayon process (crates/mccfr/src/solver/solver.rs:225-240, crates/elkan/src/elkan.rs:80-168);
+ * SURVEY §8b/§8e shard it across the GPUs of one box.  A communicator is this process's rank in that job.  The exchange
+ * step of every sharded path runs INSIDE the library on the handle's stream once a communicator is attached
+ * (rbp_nlhe_attach_comm, rbp_kmeans_attach_comm, rbp_solver_attach_comm): the host only distributes the 128-byte id.
+ * NCCL (libnccl.so.2, located with dlopen: RBP_NCCL_LIB, then the loader path) carries the bootstrap, the barriers and
+ * the plain collectives; the NLHE record/row exchange is written by the library's own kernels into peer memory mapped
+ * over NVLink (CUDA IPC).  rbp_comm_unique_id is called on ONE rank; every rank then calls rbp_comm_init with that id. */
+typedef struct rbp_comm rbp_comm_t;
+int rbp_comm_unique_id(uint8_t out[128]);
+int rbp_comm_init(int world_rank, int world_size, const uint8_t id[128], int device, rbp_comm_t** out);
+void rbp_comm_destroy(rbp_comm_t* c); /* after every handle attached to it */
+int rbp_comm_rank(rbp_comm_t* c);
+int rbp_comm_size(rbp_comm_t* c);
+int rbp_comm_barrier(rbp_comm_t* c); /* host-blocking: all ranks have reached it */
+
 /* ─────────────────────────────── MCCFR ─────────────────────────────── */
 
 /* crates/mccfr/src/solver/encounter.rs:21-27 — one (infoset, action) row, 16 B, same field order */
@@ -156,11 +173,23 @@ int rbp_nlhe_set_stream(rbp_nlhe_t* s, void* cuda_stream);
  * fold in tree order (one schedule application per Decisions), advance the epoch */
 int rbp_nlhe_step(rbp_nlhe_t* s, uint64_t n_epochs);
 /* rbp_nlhe_step with CUDA-event timing per phase (summed over the epochs): ms[0] total, [1] tree build (level expansion,
- * size/preorder sweeps, scatter), [2] value kernel, [3] resolve + radix sort, [4] fold */
-int rbp_nlhe_step_timed(rbp_nlhe_t* s, uint64_t n_epochs, int flush_l2, float ms[5]);
+ * size/preorder sweeps, scatter), [2] value kernels, [3] resolve + radix sort, [4] fold, and with a communicator [5] records
+ * to their owners (incl. barrier), [6] touched rows to every peer (incl. barrier) + install; [7] reserved.  flush_l2: one
+ * untimed 192 MiB write before the first epoch of the call (with a communicator followed by a barrier, so ranks start together). */
+int rbp_nlhe_step_timed(rbp_nlhe_t* s, uint64_t n_epochs, int flush_l2, float ms[8]);
+/* Sharded `Solver::step`: rank r samples tree ids [r*batch, (r+1)*batch) of every epoch (global batch = world*batch trees,
+ * folded in tree order exactly as one process would: solver.rs:96-105) and owns the infosets with hash(key) mod world == r.
+ * Per epoch, on the handle's stream and without host involvement: update records are stored into their owner's memory by
+ * the partition kernel itself, the owner folds them, the touched rows are stored into every peer's memory and installed —
+ * after which every rank's table holds the rows of ONE process running world*batch trees, bit for bit.  Collective call.
+ * After it, rbp_nlhe_step / rbp_nlhe_step_timed run the sharded epoch.  Needs table_slots <= 2^27. */
+int rbp_nlhe_attach_comm(rbp_nlhe_t* s, rbp_comm_t* c);
 /* out[0] epochs, [1] nodes, [2] Decisions ("infos"), [3] infoset-action regret updates, [4] table rows in use,
  * [5] update records of the last epoch, [6] largest tree of the run (nodes), [7] reserved */
 int rbp_nlhe_counters(rbp_nlhe_t* s, uint64_t out[8]);
+/* decision nodes visited while sampling, cumulative — the profile reads of SURVEY §8d's algorithmic-bytes model: out[0] walker
+ * decision nodes, [1] sum of their choice counts A, [2] opponent decision nodes, [3] sum of their A */
+int rbp_nlhe_traffic_counters(rbp_nlhe_t* s, uint64_t out[4]);
 /* One row of the reference's blueprint table (crates/nlhe/src/profile.rs:143-160: past, present, choices, edge, weight,
  * regret, payoff, visits) */
 typedef struct {

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "build", "librbp_oracle.so")
+# RBP_ORACLE_LIB: bench.py's CPU legs point this at the -O3 -march=native build made on the timing host (build.build_oracle(native=True))
+LIB_PATH = os.environ.get("RBP_ORACLE_LIB") or os.path.join(_HERE, "build", "librbp_oracle.so")
 
 ROW_DTYPE = np.dtype([("info_key", "<u4"), ("action", "<u4"), ("weight", "<f4"), ("regret", "<f4"), ("payoff", "<f4"),
                       ("visits", "<u4")])

@@ -21,11 +21,13 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "games.hpp"
+#include "pool.hpp"
 #include "rng.hpp"
 
 namespace orc {
@@ -232,6 +234,7 @@ struct Solver {
     Profile<G> profile;
     int regret_sched = R_FLOORED, weight_sched = W_LINEAR, sampling = S_EXTERNAL;
     int batch = 1, threads = 1, fold_mode = FOLD_ORDERED, fold_block = 128;
+    mutable std::shared_ptr<Pool> pool;  // rayon's persistent pool (created on first use)
     int world_rank = 0, world_size = 1;
     std::vector<uint32_t> info_order;  // all decision infosets of the game, ascending key: index space of Partial buffers
     Draw rng{0};
@@ -415,27 +418,23 @@ struct Solver {
     std::vector<Decisions> run_batch(uint64_t* node_count) const {
         int T = threads < 1 ? 1 : threads;
         if (T > batch) T = batch;
-        std::vector<std::vector<Decisions>> parts(T);
-        std::vector<uint64_t> ncount(T, 0);
-        auto work = [&](int t) {
-            int lo = (int)((int64_t)batch * t / T), hi = (int)((int64_t)batch * (t + 1) / T);
-            for (int i = lo; i < hi; ++i) {
+        if (!pool || pool->size() != T) pool = std::make_shared<Pool>(T);
+        constexpr int kChunk = 256;  // trees per claimed chunk (small-game trees are ~20 nodes)
+        const int chunks = (batch + kChunk - 1) / kChunk;
+        std::vector<std::vector<Decisions>> parts(chunks);
+        std::vector<uint64_t> ncount(chunks, 0);
+        pool->run(chunks, [&](int c, int) {
+            for (int i = c * kChunk; i < std::min(batch, (c + 1) * kChunk); ++i) {
                 const int id = world_rank * batch + i;
                 Tree<G> tree = build(root_of(id), id, sampling);
-                ncount[t] += tree.n();
-                tree_decisions(tree, parts[t]);
+                ncount[c] += tree.n();
+                tree_decisions(tree, parts[c]);
             }
-        };
-        if (T == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < T; ++t) th.emplace_back(work, t);
-            for (auto& x : th) x.join();
-        }
+        });
         std::vector<Decisions> all;
-        for (int t = 0; t < T; ++t) {
-            all.insert(all.end(), parts[t].begin(), parts[t].end());
-            *node_count += ncount[t];
+        for (int c = 0; c < chunks; ++c) {
+            all.insert(all.end(), parts[c].begin(), parts[c].end());
+            *node_count += ncount[c];
         }
         return all;
     }

@@ -27,12 +27,14 @@
 #include <cstdint>
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "iso.hpp"
 #include "mccfr.hpp"
+#include "pool.hpp"
 
 namespace orc {
 namespace nlhe {
@@ -398,6 +400,7 @@ struct Solver {
     uint64_t epochs = 0;
     Hyper hyper;
     int regret_sched = R_LINEAR, weight_sched = W_LINEAR, sampling = S_PLURIBUS, batch = 128, threads = 1;
+    std::unique_ptr<Pool> pool;  // rayon's persistent pool (created on first use)
     int world_rank = 0, world_size = 1;  // this handle samples tree ids [rank*batch, (rank+1)*batch) of a world_size*batch epoch
     Draw rng{0};
     uint64_t nodes = 0, infos = 0, updates = 0;
@@ -584,20 +587,21 @@ struct Solver {
     }
     // solver.rs:225-240 batch: this rank's trees → Decisions (tree order, first-seen infoset order inside a tree)
     std::vector<Dec> sample_decs() {
-        int T = threads < 1 ? 1 : (threads > batch ? batch : threads);
-        std::vector<std::vector<Dec>> parts(T);
-        std::vector<uint64_t> nc(T, 0);
-        auto work = [&](int th) {
-            for (int i = (int)((int64_t)batch * th / T); i < (int)((int64_t)batch * (th + 1) / T); ++i) {
+        const int T = threads < 1 ? 1 : (threads > batch ? batch : threads);
+        if (!pool || pool->size() != T) pool = std::make_unique<Pool>(T);
+        constexpr int kChunk = 16;  // trees per claimed chunk
+        const int chunks = (batch + kChunk - 1) / kChunk;
+        std::vector<std::vector<Dec>> parts(chunks);
+        std::vector<uint64_t> nc(chunks, 0);
+        pool->run(chunks, [&](int c, int) {
+            for (int i = c * kChunk; i < std::min(batch, (c + 1) * kChunk); ++i) {
                 const TreeN t = build(world_rank * batch + i);
-                nc[th] += t.game.size();
-                tree_decisions(t, parts[th]);
+                nc[c] += t.game.size();
+                tree_decisions(t, parts[c]);
             }
-        };
-        if (T == 1) work(0);
-        else { std::vector<std::thread> th; for (int k = 0; k < T; ++k) th.emplace_back(work, k); for (auto& x : th) x.join(); }
+        });
         std::vector<Dec> all;
-        for (int k = 0; k < T; ++k) { nodes += nc[k]; all.insert(all.end(), parts[k].begin(), parts[k].end()); }
+        for (int c = 0; c < chunks; ++c) { nodes += nc[c]; all.insert(all.end(), parts[c].begin(), parts[c].end()); }
         return all;
     }
     // solver.rs:96-105: every Decisions of the epoch (all ranks'), applied in global tree order

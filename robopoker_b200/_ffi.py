@@ -130,6 +130,15 @@ def load_library():
     l.rbp_nlhe_records.argtypes = [vp, P(vp), P(u64), P(u64), P(i32)]
     l.rbp_nlhe_fold_records.argtypes = [vp, vp, u64]
     l.rbp_nlhe_debug_tree.argtypes = [vp, i32, vp, i32, P(i32)]
+    l.rbp_comm_unique_id.argtypes = [vp]
+    l.rbp_comm_init.argtypes = [i32, i32, vp, i32, P(vp)]
+    l.rbp_comm_destroy.argtypes = [vp]
+    l.rbp_comm_destroy.restype = None
+    l.rbp_comm_rank.argtypes = [vp]
+    l.rbp_comm_size.argtypes = [vp]
+    l.rbp_comm_barrier.argtypes = [vp]
+    l.rbp_nlhe_attach_comm.argtypes = [vp, vp]
+    l.rbp_nlhe_traffic_counters.argtypes = [vp, P(u64)]
     _lib = l
     return l
 

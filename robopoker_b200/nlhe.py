@@ -47,6 +47,12 @@ class Nlhe:
     def set_world(self, rank, size):
         _ffi.check(self._lib.rbp_nlhe_set_world(self._h, rank, size), "rbp_nlhe_set_world")
 
+    def attach_comm(self, comm):
+        """Sharded `Solver::step` inside the library (`robopoker_b200.comm.Comm`); collective."""
+        _ffi.check(self._lib.rbp_nlhe_attach_comm(self._h, comm._h), "rbp_nlhe_attach_comm")
+        self._comm = comm  # keep it alive
+        return self
+
     def set_stream(self, cuda_stream):
         _ffi.check(self._lib.rbp_nlhe_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "rbp_nlhe_set_stream")
 
@@ -59,8 +65,9 @@ class Nlhe:
         return self.step(trees // self.batch)
 
     def step_timed(self, n=1, flush_l2=True):
-        """Returns device ms (total, tree build, value kernel, resolve+sort, fold) summed over n epochs."""
-        ms = (ctypes.c_float * 5)()
+        """Returns device ms (total, tree build, value kernels, resolve+sort, fold, records exchange, rows exchange, -) summed
+        over n epochs; the last three are zero without a communicator."""
+        ms = (ctypes.c_float * 8)()
         _ffi.check(self._lib.rbp_nlhe_step_timed(self._h, n, int(flush_l2), ms), "rbp_nlhe_step_timed")
         return tuple(ms)
 
@@ -68,6 +75,11 @@ class Nlhe:
         out = (ctypes.c_uint64 * 8)()
         _ffi.check(self._lib.rbp_nlhe_counters(self._h, out), "rbp_nlhe_counters")
         return dict(zip(("epochs", "nodes", "infos", "updates", "rows", "records", "max_tree"), (int(x) for x in out)))
+
+    def traffic_counters(self):
+        out = (ctypes.c_uint64 * 4)()
+        _ffi.check(self._lib.rbp_nlhe_traffic_counters(self._h, out), "rbp_nlhe_traffic_counters")
+        return dict(zip(("walker_nodes", "walker_choices", "opponent_nodes", "opponent_choices"), (int(x) for x in out)))
 
     def profile(self):
         n = ctypes.c_uint64()
