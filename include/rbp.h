@@ -340,6 +340,18 @@ int rbp_kmeans_timed(rbp_kmeans_t* h, int what, int iters, float* ms_out);
  * exp terms = Σ over solves of nx·ny·(2·sweeps + 1)} (the unit the flop layer's throughput is reported in); out3 nullable */
 int rbp_kmeans_sinkhorn_stats(rbp_kmeans_t* h, uint64_t* out3, int reset);
 
+/* SINKHORN layers: tensor-core screen of the two naive N x K sweeps — `Elkan::init_bounds` (crates/elkan/src/elkan.rs:39-47,68-77) and
+ * `Layer::lookup` (crates/lloyd/src/layer.rs:62-84) — which need per point only argmin_j and that one distance.  With margin >= 0,
+ * rbp_kmeans_init_bounds / rbp_kmeans_assign first compute an APPROXIMATE divergence of every point to every centroid in the
+ * scaling domain (u = e^phi, v = e^psi, Gibbs kernel exp(-C/T); the softmin half-steps of sinkhorn.rs:96-129 as bf16 hi+lo x bf16
+ * GEMMs on tcgen05 tensor cores with TMEM accumulators and a TMA-staged centroid tile: csrc/sk_screen.cuh) and then run the exact
+ * log-domain solver only for the centroids within `margin` of the point's smallest approximate value, in centroid order with
+ * the reference's first-minimum rule.  Assignments and winning distances equal the full exact sweep bit for bit whenever
+ * margin >= 2 x the screen's error; rbp_kmeans_screen_probe measures that error (approximate divergences of points [0, m) to all
+ * k centroids: out[m][k]; stats2 = {(point, 128-centroid tile) problems, Sinkhorn iterations summed}).  margin < 0 switches it off. */
+int rbp_kmeans_screen(rbp_kmeans_t* h, float margin);
+int rbp_kmeans_screen_probe(rbp_kmeans_t* h, int64_t m, float* out, uint64_t* stats2 /* nullable */);
+
 /* `Metric::emd` / `Sinkhorn::divergence` (crates/lloyd/src/metric.rs:109-115, sinkhorn.rs:166-171) for explicit pairs:
  * out[t] = max(0, OT(A[ia[t]], B[ib[t]]) - OT(A,A)/2 - OT(B,B)/2) over dense u32 histograms a_counts[na][bins],
  * b_counts[nb][bins].  Log-domain Sinkhorn exactly as sinkhorn.rs:77-139 (defaults T=0.025, 128 iterations, tol 5e-4,

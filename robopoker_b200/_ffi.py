@@ -94,6 +94,8 @@ def load_library():
     if hasattr(l, "rbp_kmeans_sinkhorn_stats"):
         l.rbp_kmeans_sinkhorn_stats.argtypes = [vp, vp, i32]
     l.rbp_measure_fadd_peak.argtypes = [f32p]
+    l.rbp_kmeans_screen.argtypes = [vp, ctypes.c_float]
+    l.rbp_kmeans_screen_probe.argtypes = [vp, i64, vp, vp]
     l.rbp_kmeans_set_metric.argtypes = [vp, vp, i32]
     l.rbp_sinkhorn_batch.argtypes = [vp, i32, vp, i32, i32, vp, vp, i64, vp, ctypes.c_float, i32, ctypes.c_float, vp]
     l.rbp_isoset_create.argtypes = [i32, i32, P(vp)]

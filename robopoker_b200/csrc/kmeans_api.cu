@@ -36,6 +36,8 @@ int sk_metric(KmSk*, float*);
 int sk_bounds(KmSk*, uint32_t*, float*, float*, uint8_t*);
 int sk_timed(KmSk*, int, int, float*);
 int sk_stats(KmSk*, uint64_t*, int);
+int sk_screen(KmSk*, float);
+int sk_screen_probe(KmSk*, int64_t, float*, uint64_t*);
 int sk_batch(const uint32_t*, int, const uint32_t*, int, int, const int32_t*, const int32_t*, int64_t, const float*, float, int, float, float*);
 }  // namespace rbp
 using namespace rbp;
@@ -135,6 +137,16 @@ int rbp_kmeans_sinkhorn_stats(rbp_kmeans_t* h, uint64_t* out3, int reset) {
     if (!h) return RBP_ERR_INVALID;
     if (h->kind != RBP_KMEANS_SINKHORN) { set_last_error("only Sinkhorn layers count OT solves"); return RBP_ERR_STATE; }
     return sk_stats(SK(h), out3, reset);
+}
+int rbp_kmeans_screen(rbp_kmeans_t* h, float margin) {
+    if (!h) return RBP_ERR_INVALID;
+    if (h->kind != RBP_KMEANS_SINKHORN) { set_last_error("the screen belongs to Sinkhorn layers (the W1 layer's distance is already exact and cheap)"); return RBP_ERR_STATE; }
+    return sk_screen(SK(h), margin);
+}
+int rbp_kmeans_screen_probe(rbp_kmeans_t* h, int64_t m, float* out, uint64_t* stats2) {
+    if (!h) return RBP_ERR_INVALID;
+    if (h->kind != RBP_KMEANS_SINKHORN) return RBP_ERR_STATE;
+    return sk_screen_probe(SK(h), m, out, stats2);
 }
 int rbp_sinkhorn_batch(const uint32_t* a_counts, int na, const uint32_t* b_counts, int nb, int bins, const int32_t* ia, const int32_t* ib,
                        int64_t n, const float* tri, float temperature, int iterations, float tolerance, float* out) {

@@ -13,8 +13,11 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cudaTypedefs.h>
+
 #include "kmeans_common.cuh"
 #include "sinkhorn.cuh"
+#include "sk_screen.cuh"
 
 namespace rbp {
 
@@ -190,8 +193,11 @@ __global__ void sk_set_centroid_kernel(SkDev d, const int64_t* __restrict__ pick
 }
 
 // naive argmin over all centroids with distance(c_j, x): init_bounds (elkan.rs:39-47) and lookup (layer.rs:44-60)
+// With `approx` (the tensor-core screen, sk_screen.cuh) only the centroids whose approximate divergence is within `margin` of
+// the point's smallest one are evaluated — exactly, in centroid order, with the same first-minimum rule.
 template <bool INIT_BOUNDS>
-__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_assign_kernel(SkDev d, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist) {
+__global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_assign_kernel(SkDev d, uint32_t* __restrict__ out_assign, float* __restrict__ out_dist,
+                                                                                const float* __restrict__ approx, float margin) {
     SkPoint& w = warp_scratch<SkPoint>();
     const int lane = threadIdx.x & 31;
     for (int64_t i = next_point(d, lane); i < d.n; i = next_point(d, lane)) {
@@ -199,7 +205,15 @@ __global__ void __launch_bounds__(kSkWarps * 32, kSkMinBlocks) sk_assign_kernel(
         int bestj = -1;
         w.n_a = load_point(d, i, w.idx_a, w.lnd_a, lane);                                             // nu = point, once
         const float self_i = d.p_self[i];
+        float bar = INFINITY;
+        if (approx) {
+            float amin = INFINITY;
+            for (int j = lane; j < d.k; j += 32) amin = fminf(amin, approx[(size_t)i * d.k + j]);
+            for (int o = 16; o > 0; o >>= 1) amin = fminf(amin, __shfl_xor_sync(0xFFFFFFFFu, amin, o));
+            bar = amin + margin;
+        }
         for (int j = 0; j < d.k; ++j) {
+            if (approx && approx[(size_t)i * d.k + j] > bar) continue;  // screened out (warp-uniform)
             w.n_b = load_centroid(d.ccount + (size_t)j * (d.bins + 1), d.bins, w.idx_b, w.lnd_b, lane);  // mu = centroid
             const float dist = sk_divergence(sk_solve(w.b(), w.a(), w.tile, d.tri, d.reg, d.hp, lane, d.stats), d.c_self[j], self_i);
             if (bestj < 0 || dist < best) { best = dist; bestj = j; }
@@ -330,6 +344,14 @@ struct KmSk : rbp_kmeans {
     int nb = 0, grid = 0, warps = kSkWarps, threads = kSkWarps * 32;
     size_t smem = 0, smem_wide = 0;  // dynamic shared memory of the point-class / centroid-class kernels
     bool have_metric = false, have_centroids = false, have_bounds = false;
+    // tensor-core screen of the naive sweeps (sk_screen.cuh); margin < 0 = off
+    float screen_margin = -1.0f;
+    int tiles = 0, sms = 148;
+    __nv_bfloat16 *gb = nullptr, *gch = nullptr, *gcl = nullptr;
+    float *nu_t = nullptr, *c_inv_n = nullptr, *approx = nullptr;
+    unsigned long long *squeue = nullptr, *sstats = nullptr;
+    CUtensorMap nu_map{};
+    std::vector<float> host_metric, host_reg;  // the dense tables (kept for the screen's bf16 Gibbs kernel)
 };
 
 namespace rbp {
@@ -428,6 +450,7 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     // override it for tuning runs
     int sms = 148, blocks_per_sm = 3;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->sms = sms;
     if (const char* e = getenv("RBP_SK_WARPS")) h->warps = std::max(1, std::min(kSkWarps, atoi(e)));
     if (const char* e = getenv("RBP_SK_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, std::min(16, atoi(e)));
     h->threads = h->warps * 32;
@@ -448,7 +471,9 @@ int sk_set_metric(KmSk* h, const float* tri, int bins) {
     if (!h || !tri || bins != h->d.bins) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
     if (!sk_metric_valid(tri, bins)) { set_last_error("ground metric entries must be finite and non-negative"); return RBP_ERR_INVALID; }
-    std::vector<float> metric((size_t)kSkLd * kSkLd), reg((size_t)kSkLd * kSkLd);
+    std::vector<float>& metric = h->host_metric;
+    std::vector<float>& reg = h->host_reg;
+    metric.assign((size_t)kSkLd * kSkLd, 0.0f); reg.assign((size_t)kSkLd * kSkLd, 0.0f);
     sk_dense_tables(tri, bins, h->d.hp.temperature, metric.data(), reg.data());
     RBP_CUDA(cudaMemcpyAsync(h->tri_dev, metric.data(), metric.size() * 4, cudaMemcpyHostToDevice, h->stream));
     RBP_CUDA(cudaMemcpyAsync(h->reg_dev, reg.data(), reg.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -499,11 +524,131 @@ int sk_set_centroids(KmSk* h, const uint64_t* counts) {
     return RBP_OK;
 }
 
+// the screen's view of the centroids: nu^T[tile][y][j] = density of bucket y in centroid tile*128 + j (bins.rs:58-60), and 1 / |support|
+__global__ void __launch_bounds__(256)
+sk_screen_prepare_kernel(const unsigned long long* __restrict__ ccount, int k, int bins, int tiles, float* __restrict__ nu_t, float* __restrict__ c_inv_n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = tiles * skt::kBinsT * skt::kLanes;
+    if (t < total) {
+        const int j = t % skt::kLanes, y = (t / skt::kLanes) % skt::kBinsT, tile = t / (skt::kLanes * skt::kBinsT), c = tile * skt::kLanes + j;
+        float v = 0.0f;
+        if (c < k && y < bins) {
+            const unsigned long long* row = ccount + (size_t)c * (bins + 1);
+            if (row[y]) v = (float)row[y] / (float)row[bins];
+        }
+        nu_t[t] = v;
+    }
+    if (t < tiles * skt::kLanes) {
+        int n = 0;
+        if (t < k) for (int y = 0; y < bins; ++y) n += ccount[(size_t)t * (bins + 1) + y] != 0ull;
+        c_inv_n[t] = n ? 1.0f / (float)n : 0.0f;
+    }
+}
+namespace {
+int screen_setup(KmSk* h) {  // buffers, the bf16 Gibbs kernel and the TMA descriptor of the centroid tile
+    if (h->approx) return RBP_OK;
+    const SkDev& d = h->d;
+    h->tiles = (d.k + skt::kLanes - 1) / skt::kLanes;
+    int st;
+    if ((st = salloc(h, (size_t)skt::kBinsT * skt::kBinsT, &h->gb))) return st;
+    if ((st = salloc(h, (size_t)skt::kBinsT * skt::kBinsT, &h->gch))) return st;
+    if ((st = salloc(h, (size_t)skt::kBinsT * skt::kBinsT, &h->gcl))) return st;
+    if ((st = salloc(h, (size_t)h->tiles * skt::kBinsT * skt::kLanes, &h->nu_t))) return st;
+    if ((st = salloc(h, (size_t)h->tiles * skt::kLanes, &h->c_inv_n))) return st;
+    if ((st = salloc(h, (size_t)h->tiles, &h->squeue))) return st;
+    if ((st = salloc(h, 4, &h->sstats))) return st;
+    if ((st = salloc(h, (size_t)d.n * d.k, &h->approx))) return st;
+    // G = exp(-C/T) rounded once to bf16 (a fixed perturbation of the cost by <= T * 2^-9), and G∘C as bf16 hi + lo planes
+    std::vector<__nv_bfloat16> gb((size_t)skt::kBinsT * skt::kBinsT), gh(gb.size()), gl(gb.size());
+    for (size_t t = 0; t < gb.size(); ++t) {
+        const __nv_bfloat16 g = __float2bfloat16_rn((float)std::exp(-(double)h->host_reg[t]));
+        const float gc = __bfloat162float(g) * h->host_metric[t];
+        gb[t] = g;
+        gh[t] = __float2bfloat16_rn(gc);
+        gl[t] = __float2bfloat16_rn(gc - __bfloat162float(gh[t]));
+    }
+    RBP_CUDA(cudaMemcpyAsync(h->gb, gb.data(), gb.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    RBP_CUDA(cudaMemcpyAsync(h->gch, gh.data(), gh.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    RBP_CUDA(cudaMemcpyAsync(h->gcl, gl.data(), gl.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    // TMA descriptor: nu^T as a 2-D fp32 tensor [tiles * 256 rows][128], boxes of 128 x 128 (the driver entry point is fetched
+    // through the runtime: the library does not link libcuda)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RBP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return RBP_ERR_CUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)skt::kLanes, (cuuint64_t)h->tiles * skt::kBinsT};
+    const cuuint64_t strides[1] = {(cuuint64_t)skt::kLanes * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)skt::kLanes, 128u}, estr[2] = {1u, 1u};
+    const CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn)(&h->nu_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->nu_t, dims, strides, box, estr,
+                                                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return RBP_ERR_CUDA; }
+    RBP_CUDA(cudaFuncSetAttribute((const void*)skt::sk_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skt::kSmemTotal));
+    return RBP_OK;
+}
+// approximate divergences of points [0, m) against every current centroid → h->approx[m][k]
+int screen_run(KmSk* h, int64_t m) {
+    int st = screen_setup(h);
+    if (st) return st;
+    const SkDev& d = h->d;
+    RBP_CUDA(cudaMemsetAsync(h->squeue, 0, (size_t)h->tiles * 8, h->stream));
+    const int total = h->tiles * skt::kBinsT * skt::kLanes;
+    sk_screen_prepare_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(d.ccount, d.k, d.bins, h->tiles, h->nu_t, h->c_inv_n);
+    RBP_LAUNCHED();
+    skt::ScreenArgs a{};
+    a.n = m; a.k = d.k; a.tiles = h->tiles; a.iterations = d.hp.iterations; a.tolerance = d.hp.tolerance;
+    a.p_idx = d.p_idx; a.p_cnt = d.p_cnt; a.p_n = d.p_n; a.p_w = d.p_w; a.pt_stride = kPtMax;
+    a.p_self = d.p_self; a.c_self = d.c_self; a.gb = h->gb; a.gch = h->gch; a.gcl = h->gcl; a.c_inv_n = h->c_inv_n;
+    a.approx = h->approx; a.queue = h->squeue; a.stats = h->sstats;
+    if (const char* e = getenv("RBP_SCREEN_DEBUG")) a.debug = atoi(e);
+    const int grid = std::max(h->tiles, (h->sms / h->tiles) * h->tiles);  // one CTA per SM (all of TMEM, 182 KB of shared memory), a multiple of the tile count
+    skt::sk_screen_kernel<<<grid, skt::kLanes, skt::kSmemTotal, h->stream>>>(h->nu_map, a);
+    RBP_LAUNCHED();
+    return RBP_OK;
+}
+// a pipeline time-out inside the screen kernel (a barrier that never completed) is an error, never a silent fallback
+int screen_check(KmSk* h) {
+    unsigned long long code = 0;
+    RBP_CUDA(cudaMemcpyAsync(&code, h->sstats + 2, 8, cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    if (code) {
+        static const char* stage[] = {"", "TMA load of the centroid tile", "centroid-side MMA", "point-side MMA", "cost MMA"};
+        set_last_error(std::string("sk_screen_kernel: time-out waiting for the ") + stage[(code >> 32) & 7] + " at point " + std::to_string((unsigned)(code & 0xFFFFFFFFu)));
+        return RBP_ERR_CUDA;
+    }
+    return RBP_OK;
+}
+}  // namespace
+
+int sk_screen(KmSk* h, float margin) {
+    if (!h->have_metric) { set_last_error("set the ground metric first"); return RBP_ERR_STATE; }
+    if (h->d.bins > skt::kBinsT) return RBP_ERR_CAPACITY;
+    RBP_CUDA(cudaSetDevice(h->device));
+    if (margin >= 0.0f) { const int st = screen_setup(h); if (st) return st; }
+    h->screen_margin = margin;
+    return RBP_OK;
+}
+int sk_screen_probe(KmSk* h, int64_t m, float* out, uint64_t* stats2) {
+    if (!h->have_centroids || !out || m < 1 || m > h->d.n) return RBP_ERR_INVALID;
+    RBP_CUDA(cudaSetDevice(h->device));
+    int st = screen_setup(h);
+    if (st) return st;
+    RBP_CUDA(cudaMemsetAsync(h->sstats, 0, 32, h->stream));
+    if ((st = screen_run(h, m))) return st;
+    RBP_CUDA(cudaMemcpyAsync(out, h->approx, (size_t)m * h->d.k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (stats2) RBP_CUDA(cudaMemcpyAsync(stats2, h->sstats, 16, cudaMemcpyDeviceToHost, h->stream));
+    RBP_CUDA(cudaStreamSynchronize(h->stream));
+    return screen_check(h);
+}
+
 int sk_init_bounds(KmSk* h) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
+    const bool screened = h->screen_margin >= 0.0f;
+    if (screened) { int st = screen_run(h, h->d.n); if (st) return st; if ((st = screen_check(h))) return st; }
     RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
-    sk_assign_kernel<true><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, nullptr, nullptr);
+    sk_assign_kernel<true><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, nullptr, nullptr, screened ? h->approx : nullptr, h->screen_margin);
     RBP_LAUNCHED();
     h->d.pending = 0;
     RBP_CUDA(cudaStreamSynchronize(h->stream));
@@ -551,8 +696,10 @@ int sk_step_finish(KmSk* h, float* drift_out, uint32_t* sizes_out, uint32_t* rea
 int sk_assign(KmSk* h, uint32_t* assign_out, float* dist_out) {
     if (!h->have_centroids) return RBP_ERR_STATE;
     RBP_CUDA(cudaSetDevice(h->device));
+    const bool screened = h->screen_margin >= 0.0f;
+    if (screened) { int st = screen_run(h, h->d.n); if (st) return st; if ((st = screen_check(h))) return st; }
     RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
-    sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+    sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist, screened ? h->approx : nullptr, h->screen_margin);
     RBP_LAUNCHED();
     RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (dist_out) RBP_CUDA(cudaMemcpyAsync(dist_out, h->tmp_dist, h->d.n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -633,7 +780,7 @@ int sk_timed(KmSk* h, int what, int iters, float* ms_out) {
         if (what == 0) { st = sk_step_local(h); if (!st) st = sk_step_finish(h, nullptr, nullptr, nullptr); }
         else {
             RBP_CUDA(cudaMemsetAsync(h->d.queue, 0, 8, h->stream));
-            sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
+            sk_assign_kernel<false><<<h->grid, h->threads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist, nullptr, 0.0f);
             g_launches.fetch_add(1);
             st = cudaGetLastError() == cudaSuccess ? RBP_OK : RBP_ERR_CUDA;
         }

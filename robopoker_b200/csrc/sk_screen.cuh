@@ -39,16 +39,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm v
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+// bounded: a descriptor or pipeline mistake must surface as an error code, not as a hung GPU (returns false after ~0.2 s)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > 400000000ll) return false;
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -146,7 +153,8 @@ struct ScreenArgs {
     const float* c_inv_n;      // [tiles * 128] 1 / |support| of the centroid; 0 = padding lane or empty centroid
     float* approx;             // [n][k] approximate divergences (NaN-free: a failed column reads 0 = "always a candidate")
     unsigned long long* queue; // [tiles] next unclaimed point of each tile's stream
-    unsigned long long* stats; // [0] (point, tile) problems, [1] iterations summed over them
+    int debug;                 // bring-up: stop after 1 = barriers + TMEM allocation, 2 = + TMA load, 3 = + TMEM store/load round trip, 4 = + the first MMA
+    unsigned long long* stats; // [0] (point, tile) problems, [1] iterations summed over them, [2] first pipeline time-out (0 = none): stage << 32 | point
 };
 
 // One CTA = one centroid tile (its nu^T staged once by TMA) x a stream of points.
@@ -172,18 +180,43 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);                // this warp's quadrant of TMEM lanes
+    if (a.debug == 1) {
+        if (tid == 0 && blockIdx.x == 0) a.approx[0] = __uint_as_float(tmem);
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem, 512);
+        return;
+    }
     if (tid == 0) {  // the tile's densities, once: 2 boxes of [128 y][128 j] fp32
         mbar_expect_tx(bar_tma, kSmemNu);
         tma_load_2d(s_nu, &nu_map, 0, tile * kBinsT, bar_tma);
         tma_load_2d(s_nu + 128 * kLanes, &nu_map, 0, tile * kBinsT + 128, bar_tma);
     }
-    mbar_wait(bar_tma, 0);
+    bool alive = mbar_wait(bar_tma, 0);
+    if (!alive && tid == 0) atomicCAS(&a.stats[2], 0ull, 1ull << 32);
+    if (a.debug == 2 || a.debug == 3) {
+        float sum = 0.0f;
+        if (alive) for (int y = 0; y < kBinsT; ++y) sum += s_nu[y * kLanes + tid];   // = 1 for a real centroid
+        if (a.debug == 3 && alive) {  // TMEM round trip: store 16 words, load them back
+            uint32_t w[16], r[16];
+            for (int q = 0; q < 16; ++q) w[q] = (uint32_t)(tid * 100 + q);
+            tmem_st16(lane_addr + kColQ, w);
+            tmem_st_wait();
+            tmem_ld16(lane_addr + kColQ, r);
+            tmem_ld_wait();
+            for (int q = 0; q < 16; ++q) if (r[q] != w[q]) sum = -1000.0f;
+        }
+        if (blockIdx.x < a.tiles && j < a.k) a.approx[j] = sum;
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem, 512);
+        return;
+    }
     const float inv_n = a.c_inv_n[j];
     const bool real = j < a.k && inv_n > 0.0f;
     const float self_c = j < a.k ? a.c_self[j] : 0.0f;
     uint32_t phase = 0;
     unsigned long long n_prob = 0, n_iter = 0;
-    for (;;) {
+    while (alive) {
         if (tid == 0) *s_next = atomicAdd(&a.queue[tile], 1ull);
         __syncthreads();
         const int64_t i = (int64_t)*s_next;
@@ -260,9 +293,18 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                     }
                     umma_commit(bar_mma);
                 }
-                mbar_wait(bar_mma, phase);
+                if (!mbar_wait(bar_mma, phase)) { alive = false; if (tid == 0) atomicCAS(&a.stats[2], 0ull, 2ull << 32 | (unsigned long long)i); }
+                if (!__syncthreads_and(alive)) { alive = false; break; }
                 phase ^= 1u;
                 tc_fence_after();
+                if (a.debug == 4) {  // Q[j, y] of the first half-step: (1/|supp x|) * sum_x G[x, y]
+                    uint32_t q[32];
+                    tmem_ld32(lane_addr + kColQ, q);
+                    tmem_ld_wait();
+                    if (j < a.k && i == 0 && h == 0) for (int y = 0; y < 32; ++y) a.approx[(size_t)j * 32 + y] = __uint_as_float(q[y]);
+                    alive = false;
+                    break;
+                }
                 for (int y0 = 0; y0 < 128; y0 += 32) {
                     uint32_t q[32], oh[16], ol[16], nh[16], nl[16];
                     tmem_ld32(lane_addr + kColQ + y0, q);
@@ -278,16 +320,17 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                         const float2 old = join_pair(oh[p], ol[p]);
                         err += fabsf(v0 - old.x) + fabsf(v1 - old.y);
                         split_pair(v0, v1, nh[p], nl[p]);
+                        if (frozen) { nh[p] = oh[p]; nl[p] = ol[p]; }   // a converged column keeps its iterate
                     }
-                    if (!frozen) {
-                        tmem_st16(lane_addr + kColVH + ((h * 128 + y0) >> 1), nh);
-                        tmem_st16(lane_addr + kColVL + ((h * 128 + y0) >> 1), nl);
-                    }
+                    // tcgen05.st is warp-collective (.sync.aligned): every lane stores, converged columns store what they had
+                    tmem_st16(lane_addr + kColVH + ((h * 128 + y0) >> 1), nh);
+                    tmem_st16(lane_addr + kColVL + ((h * 128 + y0) >> 1), nl);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncthreads();
             }
+            if (!alive) break;
             // point side: R = V·G, U = mu / R
             if (tid == 0) {
                 tc_fence_after();
@@ -299,7 +342,8 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                 }
                 umma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase);
+            if (!mbar_wait(bar_mma, phase)) { alive = false; if (tid == 0) atomicCAS(&a.stats[2], 0ull, 3ull << 32 | (unsigned long long)i); }
+            if (!__syncthreads_and(alive)) { alive = false; break; }
             phase ^= 1u;
             tc_fence_after();
 #pragma unroll
@@ -315,14 +359,12 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                         nu_[q] = m > 0.0f ? __fdividef(m, __uint_as_float(r[q])) : 0.0f;
                         err += fabsf(nu_[q] - u[x0 + q]);
                     }
-                    if (!frozen) {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) u[x0 + q] = nu_[q];
+                    for (int q = 0; q < 16; ++q) u[x0 + q] = frozen ? u[x0 + q] : nu_[q];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) split_pair(nu_[2 * q], nu_[2 * q + 1], hi[q], lo[q]);
-                        tmem_st8(lane_addr + kColUH + (x0 >> 1), hi);
-                        tmem_st8(lane_addr + kColUL + (x0 >> 1), lo);
-                    }
+                    for (int q = 0; q < 8; ++q) split_pair(u[x0 + 2 * q], u[x0 + 2 * q + 1], hi[q], lo[q]);
+                    tmem_st8(lane_addr + kColUH + (x0 >> 1), hi);   // warp-collective: every lane stores
+                    tmem_st8(lane_addr + kColUL + (x0 >> 1), lo);
                 }
             }
             tmem_st_wait();
@@ -331,6 +373,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
             tc_fence_before();
             if (__syncthreads_and(frozen)) { ++it; break; }
         }
+        if (!alive) break;
         // cost read-out (sinkhorn.rs:131-139): W[j, x] = sum_y V[j, y] (G∘C)[y, x];  cost = sum_x u_x W_x
         for (int t = tid; t < sxp * 32; t += kLanes) {
             const int n = t >> 5, c = t & 31;
@@ -357,7 +400,8 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
             }
             umma_commit(bar_mma);
         }
-        mbar_wait(bar_mma, phase);
+        if (!mbar_wait(bar_mma, phase)) { alive = false; if (tid == 0) atomicCAS(&a.stats[2], 0ull, 4ull << 32 | (unsigned long long)i); }
+        if (!__syncthreads_and(alive)) break;
         phase ^= 1u;
         tc_fence_after();
         float cost = 0.0f;

@@ -126,6 +126,20 @@ class Layer:
         _ffi.check(self._lib.rbp_kmeans_sinkhorn_stats(self._h, out.ctypes.data, int(reset)), "rbp_kmeans_sinkhorn_stats")
         return int(out[0]), int(out[1]), int(out[2])
 
+    def screen(self, margin):
+        """Tensor-core screen of the naive sweeps (`init_bounds`, `lookup`) of a Sinkhorn layer: exact solves only for the centroids
+        within `margin` of a point's smallest approximate divergence (csrc/sk_screen.cuh).  margin < 0 switches it off."""
+        _ffi.check(self._lib.rbp_kmeans_screen(self._h, float(margin)), "rbp_kmeans_screen")
+        return self
+
+    def screen_probe(self, m=None):
+        """Approximate divergences [m][k] of the first m points against every centroid, and (problems, iterations) counters."""
+        m = self.n if m is None else int(m)
+        out = np.zeros((m, self.k), np.float32)
+        stats = np.zeros(2, np.uint64)
+        _ffi.check(self._lib.rbp_kmeans_screen_probe(self._h, m, out.ctypes.data, stats.ctypes.data), "rbp_kmeans_screen_probe")
+        return out, (int(stats[0]), int(stats[1]))
+
     def cluster(self, iterations=32, seed=0):
         """`Layer::cluster` minus persistence: init → bounds → `iterations` Elkan steps → (lookup, metric, future)."""
         self.init_centroids(seed)
