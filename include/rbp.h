@@ -322,6 +322,10 @@ int rbp_kmeans_accumulator(rbp_kmeans_t* h, void** dev_ptr, size_t* bytes);
 int rbp_kmeans_counters(rbp_kmeans_t* h, void** dev_sizes /* u32[k] */, void** dev_reassigned /* u32[1] */);
 void* rbp_kmeans_stream(rbp_kmeans_t* h); /* cudaStream_t the kernels run on */
 int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* drift_out, uint32_t* sizes_out, uint32_t* reassigned_out);
+/* Point-sharded layers inside the library: after this call rbp_kmeans_step runs the point pass, ONE integer all-reduce (member sums, cluster
+ * sizes and the reassignment counter in one buffer) on the layer's stream, and the centroid update — identical centroids on every
+ * rank, bit for bit.  Every rank holds its own shard of the points and the same initial centroids (rbp_kmeans_set_centroids). */
+int rbp_kmeans_attach_comm(rbp_kmeans_t* h, rbp_comm_t* c);
 /* `Layer::lookup` (layer.rs:44-60): fresh naive argmin against the current centroids; dist_out nullable */
 int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* assign_out, float* dist_out);
 /* `Layer::future` payload: centroid histograms (counts[k][bins], weights[k]); either may be NULL */

@@ -1,4 +1,5 @@
 // kmeans_api.cu — the `rbp_kmeans_*` C ABI: dispatch on the layer kind (W1 turn layer / Sinkhorn flop layer).
+#include "comm.hpp"
 #include "kmeans_common.cuh"
 
 struct KmW1;
@@ -114,10 +115,36 @@ int rbp_kmeans_accumulator(rbp_kmeans_t* h, void** p, size_t* b) {
 int rbp_kmeans_counters(rbp_kmeans_t* h, void** s, void** r) { return DISPATCH(h, w1_counters(W1(h), s, r), sk_counters(SK(h), s, r)); }
 void* rbp_kmeans_stream(rbp_kmeans_t* h) { return !h ? nullptr : (h->kind == RBP_KMEANS_W1 ? w1_stream(W1(h)) : sk_stream(SK(h))); }
 int rbp_kmeans_step_finish(rbp_kmeans_t* h, float* d, uint32_t* s, uint32_t* r) { return DISPATCH(h, w1_step_finish(W1(h), d, s, r), sk_step_finish(SK(h), d, s, r)); }
+// With a communicator the point pass is followed by ONE integer all-reduce on the layer's stream: the K x (bins + 1) u64 member sums with the K
+// cluster sizes and the reassignment counter packed behind them (integer sums: exact in any order, so every rank forms bit-identical
+// centroids — elkan.rs:125-142 over point shards).
+__global__ void kmeans_pack_tallies_kernel(unsigned long long* __restrict__ tail, uint32_t* __restrict__ sizes, uint32_t* __restrict__ reassigned, int k, int unpack) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > k) return;
+    uint32_t* w = i < k ? sizes + i : reassigned;
+    if (unpack) *w = (uint32_t)tail[i]; else tail[i] = *w;
+}
 int rbp_kmeans_step(rbp_kmeans_t* h, float* d, uint32_t* s, uint32_t* r) {
     int st = rbp_kmeans_step_local(h);
     if (st) return st;
+    if (h->comm && h->comm->world > 1) {
+        void *acc = nullptr, *sizes = nullptr, *re = nullptr;
+        size_t bytes = 0;
+        if ((st = rbp_kmeans_accumulator(h, &acc, &bytes)) || (st = rbp_kmeans_counters(h, &sizes, &re))) return st;
+        cudaStream_t stream = static_cast<cudaStream_t>(rbp_kmeans_stream(h));
+        unsigned long long* tail = static_cast<unsigned long long*>(acc) + bytes / 8;
+        kmeans_pack_tallies_kernel<<<(h->k + 128) / 128, 128, 0, stream>>>(tail, static_cast<uint32_t*>(sizes), static_cast<uint32_t*>(re), h->k, 0);
+        RBP_LAUNCHED();
+        if ((st = comm::all_reduce_sum_u64(h->comm, acc, bytes / 8 + (size_t)h->k + 1, stream))) return st;
+        kmeans_pack_tallies_kernel<<<(h->k + 128) / 128, 128, 0, stream>>>(tail, static_cast<uint32_t*>(sizes), static_cast<uint32_t*>(re), h->k, 1);
+        RBP_LAUNCHED();
+    }
     return rbp_kmeans_step_finish(h, d, s, r);
+}
+int rbp_kmeans_attach_comm(rbp_kmeans_t* h, rbp_comm_t* c) {
+    if (!h || !c) return RBP_ERR_INVALID;
+    h->comm = c;
+    return RBP_OK;
 }
 int rbp_kmeans_assign(rbp_kmeans_t* h, uint32_t* a, float* d) {
     if (!a) return RBP_ERR_INVALID;

@@ -2,8 +2,11 @@
 #pragma once
 #include "common.cuh"
 
+struct rbp_comm;
 struct rbp_kmeans {  // opaque `rbp_kmeans_t`; concrete layers derive from it
     int kind = 0;
+    int k = 0;                  // clusters (for the fused exchange)
+    rbp_comm* comm = nullptr;   // rbp_kmeans_attach_comm: points are sharded over its ranks
 };
 
 namespace rbp {

@@ -394,6 +394,7 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     if (bins < 2 || bins > kSkMaxSupport || n < 1 || k < 1 || k > n || !counts) return RBP_ERR_INVALID;
     KmSk* h = new KmSk();
     h->kind = RBP_KMEANS_SINKHORN;
+    h->k = k;
     h->device = device;
     auto fail = [&](int code) { sk_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -420,8 +421,9 @@ int sk_create(int64_t n, int k, int bins, const uint8_t* counts, int device, rbp
     if ((st = supload(h, pn, &d.p_n))) return fail(st);
     if ((st = supload(h, pw, &d.p_w))) return fail(st);
     if ((st = salloc(h, (size_t)n, &d.p_self))) return fail(st);
-    if ((st = salloc(h, (size_t)k * (bins + 1), &d.ccount))) return fail(st);
-    if ((st = salloc(h, (size_t)k * (bins + 1), &d.acc))) return fail(st);
+    // (+ k + 2 words of tail room: with a communicator the tallies ride in the same all-reduce, kmeans_api.cu)
+    if ((st = salloc(h, (size_t)k * (bins + 1) + k + 2, &d.ccount))) return fail(st);
+    if ((st = salloc(h, (size_t)k * (bins + 1) + k + 2, &d.acc))) return fail(st);
     if ((st = salloc(h, (size_t)k, &d.c_self))) return fail(st);
     if ((st = salloc(h, (size_t)k, &d.new_self))) return fail(st);
     if ((st = salloc(h, (size_t)k * k, &d.pair))) return fail(st);
@@ -603,7 +605,7 @@ int screen_run(KmSk* h, int64_t m) {
     a.approx = h->approx; a.queue = h->squeue; a.stats = h->sstats;
     if (const char* e = getenv("RBP_SCREEN_DEBUG")) a.debug = atoi(e);
     const int grid = std::max(h->tiles, (h->sms / h->tiles) * h->tiles);  // one CTA per SM (all of TMEM, 182 KB of shared memory), a multiple of the tile count
-    skt::sk_screen_kernel<<<grid, skt::kLanes, skt::kSmemTotal, h->stream>>>(h->nu_map, a);
+    skt::sk_screen_kernel<<<grid, skt::kThreads, skt::kSmemTotal, h->stream>>>(h->nu_map, a);
     RBP_LAUNCHED();
     return RBP_OK;
 }

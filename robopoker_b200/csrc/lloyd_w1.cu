@@ -505,6 +505,7 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     if (rbp_device_count() <= device) { set_last_error("no CUDA device"); return RBP_ERR_NO_DEVICE; }
     KmW1* h = new KmW1();
     h->kind = RBP_KMEANS_W1;
+    h->k = k;
     h->device = device;
     auto fail = [&](int code) { w1_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -526,8 +527,9 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     if ((st = kalloc(h, (size_t)n, &d.upper))) return fail(st);
     if ((st = kalloc(h, (size_t)n, &d.assign))) return fail(st);
     if ((st = kalloc(h, (size_t)n, &d.stale))) return fail(st);
-    if ((st = kalloc(h, (size_t)k * (kBins + 1), &d.acc))) return fail(st);
-    if ((st = kalloc(h, (size_t)k * (kBins + 1), &d.ccount))) return fail(st);
+    // (+ k + 2 words of tail room: with a communicator the tallies ride in the same all-reduce, kmeans_api.cu)
+    if ((st = kalloc(h, (size_t)k * (kBins + 1) + k + 2, &d.acc))) return fail(st);
+    if ((st = kalloc(h, (size_t)k * (kBins + 1) + k + 2, &d.ccount))) return fail(st);
     if ((st = kalloc(h, (size_t)k, &d.sizes))) return fail(st);
     if ((st = kalloc(h, 1, &d.reassigned))) return fail(st);
     if ((st = kalloc(h, (size_t)n, &h->pot))) return fail(st);

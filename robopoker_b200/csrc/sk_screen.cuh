@@ -23,7 +23,8 @@
 namespace rbp {
 namespace skt {
 
-constexpr int kLanes = 128;     // centroids per tile = TMEM lanes = threads
+constexpr int kLanes = 128;     // centroids per tile = TMEM lanes
+constexpr int kThreads = 256;   // two threads per centroid column: warps w and w + 4 share TMEM lane quadrant w and split the bins
 constexpr int kBinsT = 256;     // histogram bins (KMEANS_MAX_CLUSTER_COUNT)
 constexpr int kMaxSx = 48;      // padded support of a point (flop children: 47)
 // TMEM columns (512 allocated)
@@ -158,7 +159,7 @@ struct ScreenArgs {
 };
 
 // One CTA = one centroid tile (its nu^T staged once by TMA) x a stream of points.
-__global__ void __launch_bounds__(kLanes, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* s_nu = reinterpret_cast<float*>(smem);                                  // [256 y][128 j]
@@ -171,15 +172,18 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
     unsigned long long* s_next = reinterpret_cast<unsigned long long*>(misc + 24);
     uint8_t* s_idx = misc + 64;                                                     // [64]
     float* s_mu = reinterpret_cast<float*>(misc + 128);                             // [64]
+    float* s_err = reinterpret_cast<float*>(misc + 512);                           // [128] the upper half's share of a column's L1 change
+    uint8_t* s_frozen = misc + 1024;                                                // [128] column converged (set by the lower half)
     const int tid = threadIdx.x, warp = tid >> 5, tile = blockIdx.x % a.tiles;
-    const int j = tile * kLanes + tid;                                              // this thread's centroid
+    const int col = tid & (kLanes - 1), part = tid >> 7;                            // TMEM lane = centroid column; which half of the bins
+    const int j = tile * kLanes + col;                                              // this thread's centroid
     if (tid == 0) { mbar_init(bar_tma, 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(s_tmem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);                // this warp's quadrant of TMEM lanes
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);          // this warp's quadrant of TMEM lanes
     if (a.debug == 1) {
         if (tid == 0 && blockIdx.x == 0) a.approx[0] = __uint_as_float(tmem);
         __syncthreads();
@@ -195,17 +199,17 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
     if (!alive && tid == 0) atomicCAS(&a.stats[2], 0ull, 1ull << 32);
     if (a.debug == 2 || a.debug == 3) {
         float sum = 0.0f;
-        if (alive) for (int y = 0; y < kBinsT; ++y) sum += s_nu[y * kLanes + tid];   // = 1 for a real centroid
+        if (alive) for (int y = 0; y < kBinsT; ++y) sum += s_nu[y * kLanes + col];   // = 1 for a real centroid
         if (a.debug == 3 && alive) {  // TMEM round trip: store 16 words, load them back
             uint32_t w[16], r[16];
             for (int q = 0; q < 16; ++q) w[q] = (uint32_t)(tid * 100 + q);
-            tmem_st16(lane_addr + kColQ, w);
+            tmem_st16(lane_addr + kColQ + 16 * part, w);
             tmem_st_wait();
-            tmem_ld16(lane_addr + kColQ, r);
+            tmem_ld16(lane_addr + kColQ + 16 * part, r);
             tmem_ld_wait();
             for (int q = 0; q < 16; ++q) if (r[q] != w[q]) sum = -1000.0f;
         }
-        if (blockIdx.x < a.tiles && j < a.k) a.approx[j] = sum;
+        if (blockIdx.x < a.tiles && j < a.k && (part == 0 || sum < 0.0f)) a.approx[j] = sum;
         tc_fence_before();
         __syncthreads();
         if (warp == 0) tmem_dealloc(tmem, 512);
@@ -229,14 +233,14 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
         }
         __syncthreads();
         // B1[c][n] = G[idx_n][8c .. 8c+7]; rows n >= sx are zero
-        for (int t = tid; t < sxp * 32; t += kLanes) {
+        for (int t = tid; t < sxp * 32; t += kThreads) {
             const int n = t >> 5, c = t & 31;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (n < sx) v = __ldg(reinterpret_cast<const uint4*>(a.gb + (size_t)s_idx[n] * kBinsT + c * 8));
             *reinterpret_cast<uint4*>(s_b1 + ((size_t)c * sxp + n) * 16) = v;
         }
         // B2[c][y] = G[y][idx_{8c} .. idx_{8c+7}] = G[idx][y] (symmetric)
-        for (int t = tid; t < (sxp >> 3) * kBinsT; t += kLanes) {
+        for (int t = tid; t < (sxp >> 3) * kBinsT; t += kThreads) {
             const int y = t & (kBinsT - 1), c = t >> 8;
             uint32_t w[4];
 #pragma unroll
@@ -255,7 +259,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
         for (int x = 0; x < kMaxSx; ++x) u[x] = x < sx ? u0 : 0.0f;
 #pragma unroll
         for (int x0 = 0; x0 < kMaxSx; x0 += 16) {
-            if (x0 < sxp) {
+            if (x0 < sxp && part == 0) {   // (part is warp-uniform: the TMEM accesses stay warp-collective)
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) split_pair(u[x0 + 2 * q], u[x0 + 2 * q + 1], hi[q], lo[q]);
@@ -263,11 +267,11 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                 tmem_st8(lane_addr + kColUL + (x0 >> 1), lo);
             }
         }
-        for (int y0 = 0; y0 < kBinsT; y0 += 32) {
+        for (int y0 = 128 * part; y0 < 128 * part + 128; y0 += 32) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const float v0 = s_nu[(y0 + 2 * q) * kLanes + tid] > 0.0f ? inv_n : 0.0f, v1 = s_nu[(y0 + 2 * q + 1) * kLanes + tid] > 0.0f ? inv_n : 0.0f;
+                const float v0 = s_nu[(y0 + 2 * q) * kLanes + col] > 0.0f ? inv_n : 0.0f, v1 = s_nu[(y0 + 2 * q + 1) * kLanes + col] > 0.0f ? inv_n : 0.0f;
                 split_pair(v0, v1, hi[q], lo[q]);
             }
             tmem_st16(lane_addr + kColVH + (y0 >> 1), hi);
@@ -278,6 +282,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
         tc_fence_before();
         __syncthreads();
         bool frozen = !real;
+        if (part == 0) s_frozen[col] = frozen;
         int it = 0;
         for (; it < a.iterations; ++it) {
             float err = 0.0f;
@@ -301,11 +306,11 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                     uint32_t q[32];
                     tmem_ld32(lane_addr + kColQ, q);
                     tmem_ld_wait();
-                    if (j < a.k && i == 0 && h == 0) for (int y = 0; y < 32; ++y) a.approx[(size_t)j * 32 + y] = __uint_as_float(q[y]);
+                    if (j < a.k && i == 0 && h == 0 && part == 0) for (int y = 0; y < 32; ++y) a.approx[(size_t)j * 32 + y] = __uint_as_float(q[y]);
                     alive = false;
                     break;
                 }
-                for (int y0 = 0; y0 < 128; y0 += 32) {
+                for (int y0 = 64 * part; y0 < 64 * part + 64; y0 += 32) {
                     uint32_t q[32], oh[16], ol[16], nh[16], nl[16];
                     tmem_ld32(lane_addr + kColQ + y0, q);
                     tmem_ld16(lane_addr + kColVH + ((h * 128 + y0) >> 1), oh);
@@ -314,7 +319,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
 #pragma unroll
                     for (int p = 0; p < 16; ++p) {
                         const int y = h * 128 + y0 + 2 * p;
-                        const float n0 = s_nu[y * kLanes + tid], n1 = s_nu[(y + 1) * kLanes + tid];
+                        const float n0 = s_nu[y * kLanes + col], n1 = s_nu[(y + 1) * kLanes + col];
                         const float v0 = n0 > 0.0f ? __fdividef(n0, __uint_as_float(q[2 * p])) : 0.0f;
                         const float v1 = n1 > 0.0f ? __fdividef(n1, __uint_as_float(q[2 * p + 1])) : 0.0f;
                         const float2 old = join_pair(oh[p], ol[p]);
@@ -326,6 +331,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                     tmem_st16(lane_addr + kColVH + ((h * 128 + y0) >> 1), nh);
                     tmem_st16(lane_addr + kColVL + ((h * 128 + y0) >> 1), nl);
                 }
+                if (part == 1 && h == 1) s_err[col] = err;   // the upper half's share of the column's L1 change
                 tmem_st_wait();
                 tc_fence_before();
                 __syncthreads();
@@ -348,7 +354,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
             tc_fence_after();
 #pragma unroll
             for (int x0 = 0; x0 < kMaxSx; x0 += 16) {
-                if (x0 < sxp) {
+                if (x0 < sxp && part == 0) {
                     uint32_t r[16], hi[8], lo[8];
                     tmem_ld16(lane_addr + kColR + x0, r);
                     tmem_ld_wait();
@@ -368,14 +374,20 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                 }
             }
             tmem_st_wait();
-            if (!frozen) ++n_iter;
-            frozen = frozen || !(err >= a.tolerance);   // sinkhorn.rs:85-94: stop once the L1 change of both sides is below the tolerance (NaN stops too)
+            if (part == 0) {
+                if (!frozen) ++n_iter;
+                err += s_err[col];
+                frozen = frozen || !(err >= a.tolerance);   // sinkhorn.rs:85-94: stop once the L1 change of both sides is below the tolerance (NaN stops too)
+                s_frozen[col] = frozen;
+            }
             tc_fence_before();
+            __syncthreads();
+            frozen = s_frozen[col] != 0;
             if (__syncthreads_and(frozen)) { ++it; break; }
         }
         if (!alive) break;
         // cost read-out (sinkhorn.rs:131-139): W[j, x] = sum_y V[j, y] (G∘C)[y, x];  cost = sum_x u_x W_x
-        for (int t = tid; t < sxp * 32; t += kLanes) {
+        for (int t = tid; t < sxp * 32; t += kThreads) {
             const int n = t >> 5, c = t & 31;
             uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
             if (n < sx) {
@@ -407,7 +419,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
         float cost = 0.0f;
 #pragma unroll
         for (int x0 = 0; x0 < kMaxSx; x0 += 16) {
-            if (x0 < sxp) {
+            if (x0 < sxp && part == 0) {
                 uint32_t r[16];
                 tmem_ld16(lane_addr + kColR + x0, r);
                 tmem_ld_wait();
@@ -415,7 +427,7 @@ sk_screen_kernel(const __grid_constant__ CUtensorMap nu_map, ScreenArgs a) {
                 for (int q = 0; q < 16; ++q) cost += u[x0 + q] * __uint_as_float(r[q]);
             }
         }
-        if (j < a.k) {
+        if (j < a.k && part == 0) {
             float d = cost - 0.5f * self_c - 0.5f * a.p_self[i];
             d = d > 0.0f ? d : 0.0f;                      // NaN or an empty centroid → 0: always re-evaluated exactly
             a.approx[(size_t)i * a.k + j] = real ? d : 0.0f;

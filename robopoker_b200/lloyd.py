@@ -126,6 +126,12 @@ class Layer:
         _ffi.check(self._lib.rbp_kmeans_sinkhorn_stats(self._h, out.ctypes.data, int(reset)), "rbp_kmeans_sinkhorn_stats")
         return int(out[0]), int(out[1]), int(out[2])
 
+    def attach_comm(self, comm):
+        """Point-sharded clustering inside the library: `step()` then includes the one integer all-reduce (`robopoker_b200.comm.Comm`)."""
+        _ffi.check(self._lib.rbp_kmeans_attach_comm(self._h, comm._h), "rbp_kmeans_attach_comm")
+        self._comm = comm
+        return self
+
     def screen(self, margin):
         """Tensor-core screen of the naive sweeps (`init_bounds`, `lookup`) of a Sinkhorn layer: exact solves only for the centroids
         within `margin` of a point's smallest approximate divergence (csrc/sk_screen.cuh).  margin < 0 switches it off."""

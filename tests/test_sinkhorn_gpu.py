@@ -104,3 +104,60 @@ def test_sinkhorn_counters_and_metric_validation(rbp):
         rbp.lloyd.Layer(pts, 8, metric=bad)
     with pytest.raises(rbp.RbpError):
         rbp.lloyd.sinkhorn_divergence(pts[:2], pts[:2], [0], [1], bad)
+
+
+# ── tensor-core screen of the naive sweeps (csrc/sk_screen.cuh: tcgen05 + TMEM + TMA) ─────────────────────────────────────────
+SCREEN_MARGIN = 2e-4  # >= 2 x the largest |approx - exact| the tests below allow (1e-4): then the screened sweep is exact
+
+
+@pytest.mark.parametrize("n,k,alpha,bins", [(600, 200, 0.02, 256),   # two centroid tiles (128 + 72), point supports ~12 (one K step)
+                                            (400, 64, 0.3, 256),     # one partial tile, supports ~34 (three K steps of the small operand)
+                                            (300, 130, 0.1, 200)])   # fewer bins than the tile's 256
+def test_screen_error_bound_and_exact_assignment(rbp, n, k, alpha, bins):
+    from lloyd_data import flop_mixture_histograms
+    pts = flop_mixture_histograms(n, bins, comps=k, alpha=alpha, seed=3)
+    tri = synthetic_metric(bins, 3)
+    g = rbp.lloyd.Layer(pts, k, metric=tri)
+    g.init_centroids(3)
+    g.init_bounds()
+    g.step()                                                   # centroids become merged member sums (wide supports)
+    counts, _ = g.future()
+    approx, (problems, iters) = g.screen_probe()
+    assert problems == n * ((k + 127) // 128) and iters > 0
+    m = min(n, 96)
+    ia, ib = np.repeat(np.arange(k), m).astype(np.int32), np.tile(np.arange(m), k).astype(np.int32)
+    exact = rbp.lloyd.sinkhorn_divergence(counts.astype(np.uint32), pts[:m].astype(np.uint32), ia, ib, tri).reshape(k, m).T   # distance(c_j, x)
+    assert np.all(np.isfinite(approx)) and np.max(np.abs(approx[:m] - exact)) < 1e-4
+    # the screened sweep = the exact sweep, bit for bit, with two orders of magnitude fewer OT solves
+    g.sinkhorn_stats(reset=True)
+    a0, d0 = g.lookup(with_distance=True)
+    full = g.sinkhorn_stats(reset=True)[0]
+    g.screen(SCREEN_MARGIN)
+    a1, d1 = g.lookup(with_distance=True)
+    few = g.sinkhorn_stats(reset=True)[0]
+    assert np.array_equal(a0, a1) and f32eq(d0, d1)
+    assert full == n * k and n <= few < full // 20
+
+
+def test_screened_init_bounds_equals_exact(rbp):
+    from lloyd_data import flop_mixture_histograms
+    pts = flop_mixture_histograms(500, 256, comps=150, alpha=0.05, seed=5)
+    tri = synthetic_metric(256, 5)
+    outs = []
+    for margin in (-1.0, SCREEN_MARGIN):
+        g = rbp.lloyd.Layer(pts, 150, metric=tri)
+        g.init_centroids(5)
+        g.screen(margin)
+        g.init_bounds()                                        # elkan.rs:39-47: argmin with first-minimum ties, upper = that distance
+        a, u, _, _ = g.bounds()
+        steps = [g.step() for _ in range(2)]                   # and the Elkan steps that start from those bounds
+        outs.append((a, u, steps[-1].drift, g.future()[0]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and f32eq(outs[0][1], outs[1][1])
+    assert f32eq(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+
+
+def test_screen_refuses_the_w1_layer(rbp):
+    from lloyd_data import turn_histograms
+    g = rbp.lloyd.Layer(turn_histograms(200, seed=0), 8)
+    with pytest.raises(rbp.RbpError):
+        g.screen(1e-4)
