@@ -111,6 +111,9 @@ int rbp_solver_set_stream(rbp_solver_t* s, void* cuda_stream);
 void rbp_solver_destroy(rbp_solver_t* s);
 /* `Solver::step` ×n (solver.rs:96-105) — sample `batch` trees, compute Decisions, fold, advance epoch */
 int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs);
+/* `Solver::spend` (solver.rs:130-137): step in a tight loop until `seconds` of wall clock are used; returns the epochs run and the time taken
+ * (the per-decision refinement budget of the real-time players, crates/subgame) */
+int rbp_solver_spend(rbp_solver_t* s, double seconds, uint64_t* epochs_out, double* elapsed_out);
 /* rbp_solver_step with CUDA-event timing on the library's own stream (bench.py): every epoch is bracketed by
  * events, optionally preceded by an (untimed) L2 flush; returns the summed device milliseconds of the n steps and,
  * if non-NULL, the summed durations of the sampling and fold kernels. */
@@ -172,6 +175,8 @@ int rbp_nlhe_set_stream(rbp_nlhe_t* s, void* cuda_stream);
 /* `Solver::step` x n (crates/mccfr/src/solver/solver.rs:96-105): sample `batch` trees, Decisions per walker infoset,
  * fold in tree order (one schedule application per Decisions), advance the epoch */
 int rbp_nlhe_step(rbp_nlhe_t* s, uint64_t n_epochs);
+/* `Solver::spend` for the NLHE solver (one epoch at a time) */
+int rbp_nlhe_spend(rbp_nlhe_t* s, double seconds, uint64_t* epochs_out, double* elapsed_out);
 /* rbp_nlhe_step with CUDA-event timing per phase (summed over the epochs): ms[0] total, [1] tree build (level expansion,
  * size/preorder sweeps, scatter), [2] value kernels, [3] resolve + radix sort, [4] fold, and with a communicator [5] records
  * to their owners (incl. barrier), [6] touched rows to every peer (incl. barrier) + install; [7] reserved.  flush_l2: one

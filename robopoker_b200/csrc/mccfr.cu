@@ -17,6 +17,7 @@
 // Because every f32 operation and its order match the oracle's, results are bit-identical, so the sampled
 // trajectories of GPU and oracle never diverge.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
@@ -1081,6 +1082,22 @@ int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs) {
     return RBP_OK;
 }
 
+// `Solver::spend` (crates/mccfr/src/solver/solver.rs:130-137): epochs in a tight loop until the wall-clock budget is used up —
+// what the real-time (subgame) players call with their per-decision budget
+int rbp_solver_spend(rbp_solver_t* s, double seconds, uint64_t* epochs_out, double* elapsed_out) {
+    if (!s || !(seconds >= 0.0)) return RBP_ERR_INVALID;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    uint64_t n = 0;
+    while (elapsed() < seconds) {
+        const int rc = rbp_solver_step(s, 8);  // a Kuhn / Leduc epoch is tens of microseconds: check the clock every 8
+        if (rc != RBP_OK) return rc;
+        n += 8;
+    }
+    if (epochs_out) *epochs_out = n;
+    if (elapsed_out) *elapsed_out = elapsed();
+    return RBP_OK;
+}
 int rbp_solver_step_timed(rbp_solver_t* s, uint64_t n_epochs, int flush_l2, float* ms_total, float* ms_sample, float* ms_fold) {
     if (!s || !ms_total) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(s->device));

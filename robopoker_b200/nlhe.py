@@ -61,6 +61,12 @@ class Nlhe:
         _ffi.check(self._lib.rbp_nlhe_step(self._h, n), "rbp_nlhe_step")
         return self
 
+    def spend(self, seconds):
+        """`Solver::spend` (crates/mccfr/src/solver/solver.rs:130-137); returns (epochs, elapsed seconds)."""
+        n, dt = ctypes.c_uint64(), ctypes.c_double()
+        _ffi.check(self._lib.rbp_nlhe_spend(self._h, float(seconds), ctypes.byref(n), ctypes.byref(dt)), "rbp_nlhe_spend")
+        return int(n.value), float(dt.value)
+
     def solve(self, trees):
         return self.step(trees // self.batch)
 

@@ -88,6 +88,12 @@ class Solver:
         _ffi.check(self._lib.rbp_solver_step(self._h, n), "rbp_solver_step")
         return self
 
+    def spend(self, seconds):
+        """`Solver::spend` (solver.rs:130-137): steps until the wall-clock budget is used; returns (epochs, elapsed seconds)."""
+        n, dt = ctypes.c_uint64(), ctypes.c_double()
+        _ffi.check(self._lib.rbp_solver_spend(self._h, float(seconds), ctypes.byref(n), ctypes.byref(dt)), "rbp_solver_spend")
+        return int(n.value), float(dt.value)
+
     def step_timed(self, n=1, flush_l2=True):
         """`step` × n with CUDA-event timing on the library stream; returns (total_ms, sample_ms, fold_ms)."""
         t, a, b = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()

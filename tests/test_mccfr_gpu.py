@@ -187,3 +187,38 @@ def test_rps_bit_exact(rbp, oracle, fold):
     rows_equal(g.profile_rows(), o.profile_rows())
     assert g.counters() == o.counters()
     assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32)
+
+
+def test_batched_fold_at_its_old_bench_size(rbp, oracle):
+    # the (non-reference) batched fold at 262144 trees / epoch with the flagship-of-round-1 tuple: still the oracle's sums, bit for bit
+    g = rbp.Solver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=262144, seed=0, fold=rbp.FOLD_BATCHED)
+    o = oracle.OracleSolver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=262144, seed=0, threads=8)
+    o.set_fold(1)
+    g.step(2)
+    o.step(2)
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.counters() == o.counters()
+
+
+def test_batch_one_exploitability_lock_step_to_2_16(rbp, oracle):
+    # BASELINE.json configs[1] in the reference's own regime (batch_size() = 1): the exploitability curve sampled at 2^k epochs is the oracle's, bit
+    # for bit, and ends under the reference's threshold for this many iterations (crates/leduc/src/solver.rs:121-123 asserts < 0.080 at 2^18)
+    g = rbp.Solver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=0)
+    o = oracle.OracleSolver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=0, threads=1)
+    done = 0
+    for k in range(6, 17):
+        g.step((1 << k) - done)
+        o.step((1 << k) - done)
+        done = 1 << k
+        assert np.float32(g.exploitability()).view(np.uint32) == np.float32(o.exploitability()).view(np.uint32), k
+    rows_equal(g.profile_rows(), o.profile_rows())
+    assert g.exploitability() < 0.15
+
+
+def test_spend_runs_until_the_deadline(rbp):
+    # `Solver::spend` (solver.rs:130-137): the real-time players' wall-clock budget
+    g = rbp.Solver("leduc", batch=64, seed=3)
+    n, dt = g.spend(0.2)
+    assert n > 0 and n == g.epochs and 0.2 <= dt < 1.0
+    h = rbp.Solver("leduc", batch=64, seed=3).step(n)
+    rows_equal(g.profile_rows(), h.profile_rows())   # the budgeted run is the same run

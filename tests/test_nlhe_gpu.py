@@ -81,6 +81,22 @@ def test_profile_parity_with_the_large_epoch_walker_sort(rbp, oracle, monkeypatc
         assert cg[k] == co[k], (k, cg, co)
 
 
+@pytest.mark.parametrize("batch,epochs", [(16384, 2), (65536, 1)])
+def test_profile_parity_at_bench_sizes(rbp, oracle, batch, epochs):
+    """The bench configuration itself (Flagship, seed 0, 16384 trees / epoch) and the 65536-tree epoch, where the size-dependent paths switch on by
+    themselves — the tree tie-break of the walker sort, the per-child split of large roots, hot fold segments of thousands of Decisions: blueprint
+    rows and telemetry bit-identical to the oracle."""
+    import os
+    from robopoker_b200.nlhe import Nlhe
+    g = Nlhe(batch=batch, seed=0, table_slots=1 << 22)
+    o = oracle.OracleNlhe(seed=0, batch=batch, threads=os.cpu_count() or 8)
+    g.step(epochs)
+    o.step(epochs)
+    rows_equal(g.profile(), o.export())
+    c, d = g.counters(), o.counters()
+    assert (c["epochs"], c["nodes"], c["infos"], c["updates"], c["rows"]) == (d["epochs"], d["nodes"], d["infos"], d["updates"], d["rows"])
+
+
 def test_export_import_roundtrip(rbp, oracle):
     g, o = make(rbp, oracle, 64, 3)
     g.step(3), o.step(5)

@@ -161,3 +161,21 @@ def test_screen_refuses_the_w1_layer(rbp):
     g = rbp.lloyd.Layer(turn_histograms(200, seed=0), 8)
     with pytest.raises(rbp.RbpError):
         g.screen(1e-4)
+
+
+def test_preflop_layer_is_identity_with_a_sinkhorn_metric(rbp, oracle):
+    """`Layer::init_centroids` on the preflop street (crates/lloyd/src/layer.rs:151-154): N = K = 169, every point is its own centroid; the layer's
+    outputs are the identity lookup and the 169 x 169 symmetrised Sinkhorn metric between the points (layer.rs:85-101)."""
+    from lloyd_data import flop_mixture_histograms
+    pts = flop_mixture_histograms(169, 256, comps=40, alpha=0.3, seed=9, draws=200)   # preflop points: histograms over the 256 flop clusters
+    tri = synthetic_metric(256, 9)
+    g = rbp.lloyd.Layer(pts, 169, metric=tri)
+    g.set_centroids(pts.astype(np.uint64))
+    o = oracle.OracleKmeans(pts, 169, threads=8)
+    o.set_metric(tri)
+    o.set_centroids_from_points(np.arange(169))
+    a, d = g.lookup(with_distance=True)
+    assert np.array_equal(a, np.arange(169)) and np.all(d == 0.0)      # divergence(x, x) = max(0, OT - OT/2 - OT/2) = 0, first minimum
+    assert f32eq(g.metric(), o.metric())
+    counts, weights = g.future()
+    assert np.array_equal(counts, pts.astype(np.uint64)) and np.array_equal(weights, pts.sum(axis=1).astype(np.uint64))
