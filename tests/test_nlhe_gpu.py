@@ -97,6 +97,18 @@ def test_profile_parity_at_bench_sizes(rbp, oracle, batch, epochs):
     assert (c["epochs"], c["nodes"], c["infos"], c["updates"], c["rows"]) == (d["epochs"], d["nodes"], d["infos"], d["updates"], d["rows"])
 
 
+def test_waves_do_not_change_the_result(rbp, oracle, monkeypatch):
+    """An epoch's trees are sampled in concurrent waves (two from 4096 trees on, four from 32768); forced to three at a small size here: same
+    trees, same blueprint rows."""
+    monkeypatch.setenv("RBP_NLHE_WAVES", "3")
+    g, o = make(rbp, oracle, 100, 7)
+    trees_equal(g, o, [0, 32, 33, 34, 66, 67, 99])
+    g.step(4)
+    o.step(4)
+    rows_equal(g.profile(), o.export())
+    assert g.counters()["nodes"] == o.counters()["nodes"] and g.counters()["updates"] == o.counters()["updates"]
+
+
 def test_export_import_roundtrip(rbp, oracle):
     g, o = make(rbp, oracle, 64, 3)
     g.step(3), o.step(5)
