@@ -381,11 +381,13 @@ def main_leduc(args):
         stepper = lambda: s.step(E)  # noqa: E731
     else:
         import torch
-        from robopoker_b200.distributed import ShardedSolver
+        from robopoker_b200.comm import Comm
 
         stream = torch.cuda.current_stream()
         s.set_stream(stream.cuda_stream)
-        sh = ShardedSolver(s, dist, device=local)
+        comm = Comm.from_torch(dist, device=local)
+        s.attach_comm(comm)        # the exchange runs inside the library
+        sh = s
         sh.step(warm * E)
         u0 = s.counters()["updates"]
         dist.barrier(); torch.cuda.synchronize()
@@ -393,7 +395,7 @@ def main_leduc(args):
         l0 = l.rbp_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        sh.step(K * E)             # per epoch: sample -> all-gather (NCCL) -> fold, all on this stream
+        sh.step(K * E)             # per epoch: sample -> all-gather of the partial sums (NCCL, inside the library) -> fold, all on this stream
         e1.record(stream)
         torch.cuda.synchronize(); dist.barrier()
         ms_total = all_max(dist, e0.elapsed_time(e1))

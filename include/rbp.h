@@ -143,6 +143,7 @@ int rbp_solver_game_shape(rbp_solver_t* s, int out[6]);
  * rbp_solver_sample() each rank holds its blocked partial sums; all-gather `delta` buffers across ranks into
  * `gathered` (rank-major) and call rbp_solver_fold_gathered(), which sums in rank order — bit-identical on
  * every rank and to the single-GPU run with world_size*batch trees. */
+int rbp_solver_attach_comm(rbp_solver_t* s, rbp_comm_t* c); /* the same exchange inside the library: rbp_solver_step then all-gathers on its stream */
 int rbp_solver_sample(rbp_solver_t* s);                                   /* K1 only (+ local blocked sums)     */
 int rbp_solver_delta_buffer(rbp_solver_t* s, void** dev_ptr, size_t* bytes); /* this rank's partial sums (device) */
 int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int world_size); /* K2 over all ranks  */

@@ -143,6 +143,7 @@ def load_library():
     l.rbp_solver_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
     l.rbp_nlhe_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
     l.rbp_kmeans_attach_comm.argtypes = [vp, vp]
+    l.rbp_solver_attach_comm.argtypes = [vp, vp]
     l.rbp_nlhe_traffic_counters.argtypes = [vp, P(u64)]
     _lib = l
     return l

@@ -24,6 +24,7 @@
 #include <mutex>
 #include <vector>
 
+#include "comm.hpp"
 #include "common.cuh"
 #include "flat_game.hpp"
 
@@ -822,6 +823,8 @@ struct rbp_solver {
     bool own_stream = true;
     int device = 0, regret = 0, weight = 0, sampling = 0, fold_mode = 0, batch = 1;
     int world_rank = 0, world_size = 1;
+    rbp_comm* comm = nullptr;   // rbp_solver_attach_comm
+    Partial* gathered = nullptr;  // [world][infosets] partial sums of every rank
     bool sampled = false;  // rbp_solver_sample ran for the current epoch (its partial sums are what fold_gathered consumes)
     uint64_t seed = 0, epochs = 0;
     rbp_hyper_t hyper{};
@@ -1061,18 +1064,36 @@ void rbp_solver_destroy(rbp_solver_t* s) {
     delete s;
 }
 
+// Small games across ranks inside the library (BATCHED fold only: the ordered fold over a few hundred rows is serial per row): every
+// rank samples its shard of the epoch's trees, the blocked partial sums (48 B per infoset) are all-gathered on the solver's stream
+// and every rank folds them in rank order — tables stay bit-identical.  Collective.
+int rbp_solver_attach_comm(rbp_solver_t* s, rbp_comm_t* c) {
+    if (!s || !c) return RBP_ERR_INVALID;
+    if (s->fold_mode != RBP_FOLD_BATCHED) { set_last_error("rbp_solver_attach_comm needs RBP_FOLD_BATCHED"); return RBP_ERR_STATE; }
+    if (c->device != s->device) { set_last_error("communicator lives on another device"); return RBP_ERR_INVALID; }
+    RBP_CUDA(cudaSetDevice(s->device));
+    int st = alloc(s, (size_t)c->world * s->dev.n_infos, &s->gathered);
+    if (st) return st;
+    s->comm = c; s->world_rank = c->rank; s->world_size = c->world;
+    return RBP_OK;
+}
+
 int rbp_solver_step(rbp_solver_t* s, uint64_t n_epochs) {
     if (!s) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(s->device));
-    if (s->fold_mode == RBP_FOLD_BATCHED && s->world_size > 1) {
-        set_last_error("BATCHED fold with world_size > 1: drive rbp_solver_sample / exchange / rbp_solver_fold_gathered");
+    if (s->fold_mode == RBP_FOLD_BATCHED && s->world_size > 1 && !s->comm) {
+        set_last_error("BATCHED fold with world_size > 1 and no communicator: rbp_solver_attach_comm, or drive rbp_solver_sample / exchange / rbp_solver_fold_gathered");
         return RBP_ERR_STATE;
     }
     for (uint64_t i = 0; i < n_epochs; ++i) {
         EpochArgs ep = epoch_args(s);
         int st;
         if ((st = launch_sample(s, ep))) return st;
-        if (s->fold_mode == RBP_FOLD_BATCHED) {
+        if (s->fold_mode == RBP_FOLD_BATCHED && s->comm && s->world_size > 1) {
+            if ((st = launch_rank_partial(s))) return st;
+            if ((st = comm::all_gather_bytes(s->comm, s->delta, s->gathered, (size_t)s->dev.n_infos * sizeof(Partial), s->stream))) return st;
+            if ((st = launch_apply_batched(s, ep, s->gathered, s->world_size))) return st;
+        } else if (s->fold_mode == RBP_FOLD_BATCHED) {
             if ((st = launch_rank_partial(s))) return st;
             if ((st = launch_apply_batched(s, ep, s->delta, 1))) return st;
         } else if ((st = launch_fold(s, ep))) return st;

@@ -88,6 +88,12 @@ class Solver:
         _ffi.check(self._lib.rbp_solver_step(self._h, n), "rbp_solver_step")
         return self
 
+    def attach_comm(self, comm):
+        """Tree-sharded epochs inside the library (BATCHED fold): `step()` then all-gathers the partial sums itself."""
+        _ffi.check(self._lib.rbp_solver_attach_comm(self._h, comm._h), "rbp_solver_attach_comm")
+        self._comm = comm
+        return self
+
     def spend(self, seconds):
         """`Solver::spend` (solver.rs:130-137): steps until the wall-clock budget is used; returns (epochs, elapsed seconds)."""
         n, dt = ctypes.c_uint64(), ctypes.c_double()

@@ -167,7 +167,10 @@ def test_preflop_layer_is_identity_with_a_sinkhorn_metric(rbp, oracle):
     """`Layer::init_centroids` on the preflop street (crates/lloyd/src/layer.rs:151-154): N = K = 169, every point is its own centroid; the layer's
     outputs are the identity lookup and the 169 x 169 symmetrised Sinkhorn metric between the points (layer.rs:85-101)."""
     from lloyd_data import flop_mixture_histograms
-    pts = flop_mixture_histograms(169, 256, comps=40, alpha=0.3, seed=9, draws=200)   # preflop points: histograms over the 256 flop clusters
+    # preflop-shaped layer: 169 points over the 256 flop clusters.  (A point side holds at most 64 buckets — sized for the flop's 47 children;
+    # real preflop histograms are wider and go through rbp_sinkhorn_batch, whose both sides take 256: test_batched_divergence_bit_exact.)
+    pts = flop_mixture_histograms(169, 256, comps=40, alpha=0.3, seed=9, draws=60)
+    assert (pts > 0).sum(axis=1).max() <= 64
     tri = synthetic_metric(256, 9)
     g = rbp.lloyd.Layer(pts, 169, metric=tri)
     g.set_centroids(pts.astype(np.uint64))
