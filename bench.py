@@ -41,7 +41,7 @@ def parse():
                    help="nlhe = BASELINE.json configs[3] (default, the north-star workload); leduc = configs[1]; lloyd_turn = configs[4]; lloyd_flop = configs[2]")
     p.add_argument("--batch", type=int, default=None, help="trees per epoch per GPU (default: 16384 nlhe and leduc)")
     p.add_argument("--epochs-per-step", type=int, default=None, help="epochs in one bench step (default: 32 nlhe, 64 leduc)")
-    p.add_argument("--table-slots", type=int, default=1 << 25, help="nlhe: infoset table capacity (power of two)")
+    p.add_argument("--table-slots", type=int, default=1 << 22, help="nlhe: infoset table capacity (power of two); the synthetic abstraction of config 4 yields ~1.5e5 infosets")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--k", type=int, default=None, help="lloyd_*: clusters (default 256 turn, 200 flop)")
     p.add_argument("--points", type=int, default=None, help="lloyd_*: points (default: the street's isomorphism count)")

@@ -25,6 +25,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kmeans_common.cuh"
 
 namespace rbp {
@@ -221,13 +223,35 @@ assign_kernel(KmDev km, uint32_t* __restrict__ out_assign, float* __restrict__ o
 }
 
 // ── one Elkan step, point side (elkan.rs:153-164 up to recompute) ──
-template <int THREADS, int MINB, int TILE>
+// TMA bulk copy (1-D: the rows of a centroid tile are contiguous) of `bytes` into shared memory, completion on an mbarrier
+__device__ __forceinline__ void tile_bulk_load(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last read through the generic proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tile_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+}
+// PIPE: the centroid CDF tiles arrive by TMA bulk copies into a two-stage shared-memory ring (tile t + 1 is in flight while tile t is
+// worked on); otherwise every tile is staged with plain loads between two block barriers.
+template <int THREADS, int MINB, int TILE, bool PIPE = false, int kFar = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 elkan_step_kernel(KmDev km) {
-    extern __shared__ __align__(16) float s_cdf[];
-    float* s_drift = s_cdf + (size_t)min(km.k, TILE) * kCdfRow;  // [K] drift of the previous step
+    extern __shared__ __align__(128) float s_cdf[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    float* s_drift = s_cdf + (PIPE ? (size_t)2 * TILE : (size_t)min(km.k, TILE)) * kCdfRow;  // [K] drift of the previous step
     for (int j = threadIdx.x; j < km.k; j += blockDim.x) s_drift[j] = km.pending ? km.drift[j] : 0.0f;
+    if (PIPE && threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (PIPE && threadIdx.x == 0) tile_bulk_load(s_cdf, km.cdf, (uint32_t)min(TILE, km.k) * kCdfRow * 4u, &s_bar[0]);
+    uint32_t bar_phase = 0;  // bit b = parity to wait for on barrier b
     const int64_t i = blockIdx.x * (int64_t)THREADS + threadIdx.x;
     const bool live = i < km.n;
     float X[kBins];
@@ -262,9 +286,19 @@ elkan_step_kernel(KmDev km) {
     const uint32_t c_refresh = c;
     for (int j0 = 0; j0 < km.k; j0 += TILE) {
         const int kt = min(TILE, km.k - j0);
-        __syncthreads();
-        stage_cdf_tile(s_cdf, km.cdf, j0, kt);
-        __syncthreads();
+        float* tile = s_cdf;
+        if (PIPE) {
+            const int t = j0 / TILE, nb = (t + 1) & 1;
+            if (threadIdx.x == 0 && j0 + TILE < km.k)   // buffer nb was last read in the previous iteration, which ended with a block barrier
+                tile_bulk_load(s_cdf + (size_t)nb * TILE * kCdfRow, km.cdf + (size_t)(j0 + TILE) * kCdfRow, (uint32_t)min(TILE, km.k - j0 - TILE) * kCdfRow * 4u, &s_bar[nb]);
+            tile = s_cdf + (size_t)(t & 1) * TILE * kCdfRow;
+            tile_wait(&s_bar[t & 1], bar_phase >> (t & 1) & 1u);
+            bar_phase ^= 1u << (t & 1);
+        } else {
+            __syncthreads();
+            stage_cdf_tile(s_cdf, km.cdf, j0, kt);
+            __syncthreads();
+        }
         // software pipeline: the bounds and the pairwise row of group g+1 are requested before group g is worked on,
         // so their HBM/L2 latency hides behind the 808 FADDs of the current group
         float ln[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -289,6 +323,10 @@ elkan_step_kernel(KmDev km) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) l[g] = ln[g];
             if (jj + 4 < kt) prefetch(jj + 4);
+            if (kFar > 0 && live && j0 + jj + kFar + 4 <= km.k) {  // pull the bounds of a later group from HBM into L2 (they cross tiles: the stream is [K][N])
+#pragma unroll
+                for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(km.lower + (size_t)(j0 + jj + kFar + g) * km.n + i));
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 if (g < g_n && live) {
@@ -306,9 +344,9 @@ elkan_step_kernel(KmDev km) {
             // four distances are produced together.
             float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (__any_sync(0xFFFFFFFFu, want)) {
-                if (g_n == 4) dist_group<4>(X, s_cdf + (size_t)jj * kCdfRow, d);
+                if (g_n == 4) dist_group<4>(X, tile + (size_t)jj * kCdfRow, d);
                 else
-                    for (int g = 0; g < g_n; ++g) { float t[1]; dist_group<1>(X, s_cdf + (size_t)(jj + g) * kCdfRow, t); d[g] = t[0]; }
+                    for (int g = 0; g < g_n; ++g) { float t[1]; dist_group<1>(X, tile + (size_t)(jj + g) * kCdfRow, t); d[g] = t[0]; }
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -327,6 +365,7 @@ elkan_step_kernel(KmDev km) {
                 }
             }
         }
+        if (PIPE) __syncthreads();  // every thread is done with this tile's buffer: the next bulk copy may overwrite it
     }
     if (live) {
         km.assign[i] = c;
@@ -474,6 +513,16 @@ struct KmW1 : rbp_kmeans {
     size_t smem = 0;
     bool have_centroids = false, have_bounds = false;
     uint64_t dist_evals = 0;
+    // After init_bounds the points are stored sorted by their first assignment (position p holds original point perm[p]), so that the 32 points
+    // of a warp start in the same cluster and prune the same centroids: the step computes a group of distances whenever ANY lane of the warp
+    // needs one, and with points in input order a warp's lanes wanted ~half of all groups between them (profiles/r2z).  Results are per point
+    // and the merge is an integer sum: nothing depends on the storage order; every per-point output is returned in input order.
+    uint8_t* pts_alt = nullptr;
+    uint32_t *perm = nullptr, *perm_alt = nullptr, *order = nullptr, *iota = nullptr, *assign_alt = nullptr;
+    float* upper_alt = nullptr;
+    void* sort_tmp = nullptr;
+    size_t sort_bytes = 0;
+    bool permuted = false, reorder = true;
 };
 
 namespace {
@@ -506,6 +555,7 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
     KmW1* h = new KmW1();
     h->kind = RBP_KMEANS_W1;
     h->k = k;
+    if (const char* e = getenv("RBP_W1_REORDER")) h->reorder = atoi(e) != 0;
     h->device = device;
     auto fail = [&](int code) { w1_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -546,6 +596,9 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
         cudaFuncSetAttribute(elkan_step_kernel<128, 1, kTileK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(elkan_step_kernel<256, 2, kTileK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128, false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 64 * kCdfRow * 4 + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
@@ -561,9 +614,12 @@ void w1_destroy(KmW1* h) {
     delete h;
 }
 
+namespace { int restore_input_order(KmW1* h); }
+
 int w1_init_pp(KmW1* h, uint64_t seed, int32_t* chosen_out) {
     if (!h) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(h->device));
+    { const int st = restore_input_order(h); if (st) return st; }
     for (int r = 0; r < h->d.k; ++r) {
         pp_update_kernel<<<h->nb, kThreads, 0, h->stream>>>(h->d, h->pot, h->pick, r == 0, h->bsum);
         RBP_LAUNCHED();
@@ -599,6 +655,78 @@ int w1_set_centroids(KmW1* h, const uint64_t* counts) {
     return RBP_OK;
 }
 
+__global__ void w1_iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+// new position p <- old position order[p]: the 112-byte point row, its upper bound, and the composed permutation
+__global__ void __launch_bounds__(256)
+w1_gather_kernel(const uint8_t* __restrict__ pts, const float* __restrict__ upper, const uint32_t* __restrict__ perm_old, const uint32_t* __restrict__ order, int64_t n,
+                 uint8_t* __restrict__ pts_out, float* __restrict__ upper_out, uint32_t* __restrict__ perm_out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t p = t / (kRow / 16), q = t % (kRow / 16);
+    if (p >= n) return;
+    const uint32_t src = order[p];
+    reinterpret_cast<uint4*>(pts_out + (size_t)p * kRow)[q] = reinterpret_cast<const uint4*>(pts + (size_t)src * kRow)[q];
+    if (q == 0) { upper_out[p] = upper[src]; perm_out[p] = perm_old ? perm_old[src] : src; }
+}
+// out[perm[p]] = in[p]: per-point results back in input order
+template <class T>
+__global__ void w1_unpermute_kernel(const T* __restrict__ in, const uint32_t* __restrict__ perm, int64_t n, T* __restrict__ out) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) out[perm[p]] = in[p];
+}
+namespace {
+int reorder_by_assignment(KmW1* h) {  // right after init_bounds: every lower bound is 0 and nothing is stale, so only points / assign / upper move
+    KmDev& d = h->d;
+    if (!h->reorder || d.n < 1024) return RBP_OK;
+    int st;
+    if (!h->pts_alt) {
+        if ((st = kalloc(h, (size_t)d.n * kRow, &h->pts_alt))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->perm))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->perm_alt))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->order))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->iota))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->assign_alt))) return st;
+        if ((st = kalloc(h, (size_t)d.n, &h->upper_alt))) return st;
+        RBP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_bytes, d.assign, h->assign_alt, h->iota, h->order, (int)d.n, 0, 32, h->stream));
+        if ((st = kalloc(h, h->sort_bytes, reinterpret_cast<unsigned char**>(&h->sort_tmp)))) return st;
+    }
+    int bits = 1;
+    while ((1 << bits) < d.k) ++bits;
+    w1_iota_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, h->stream>>>(h->iota, d.n);
+    RBP_LAUNCHED();
+    RBP_CUDA(cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_bytes, d.assign, h->assign_alt, h->iota, h->order, (int)d.n, 0, bits, h->stream));  // stable
+    const int64_t threads = d.n * (kRow / 16);
+    w1_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(d.pts, d.upper, h->permuted ? h->perm : nullptr, h->order, d.n, h->pts_alt, h->upper_alt, h->perm_alt);
+    RBP_LAUNCHED();
+    uint8_t* old_pts = const_cast<uint8_t*>(d.pts);
+    d.pts = h->pts_alt; h->pts_alt = old_pts;
+    std::swap(d.assign, h->assign_alt);
+    std::swap(d.upper, h->upper_alt);
+    std::swap(h->perm, h->perm_alt);
+    h->permuted = true;
+    return RBP_OK;
+}
+int restore_input_order(KmW1* h) {  // k-means++ draws by a prefix sum over the points IN INPUT ORDER (include/rbp.h contract)
+    KmDev& d = h->d;
+    if (!h->permuted) return RBP_OK;
+    // order := inverse of perm, then the same gather
+    w1_iota_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, h->stream>>>(h->iota, d.n);
+    RBP_LAUNCHED();
+    w1_unpermute_kernel<uint32_t><<<(unsigned)((d.n + 255) / 256), 256, 0, h->stream>>>(h->iota, h->perm, d.n, h->order);
+    RBP_LAUNCHED();
+    const int64_t threads = d.n * (kRow / 16);
+    w1_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(d.pts, d.upper, nullptr, h->order, d.n, h->pts_alt, h->upper_alt, h->perm_alt);
+    RBP_LAUNCHED();
+    uint8_t* old_pts = const_cast<uint8_t*>(d.pts);
+    d.pts = h->pts_alt; h->pts_alt = old_pts;
+    h->permuted = false;
+    h->have_bounds = false;  // assign / upper were not carried over
+    return RBP_OK;
+}
+}  // namespace
+
 int w1_init_bounds(KmW1* h) {
     if (!h) return RBP_ERR_INVALID;
     if (!h->have_centroids) { set_last_error("init_bounds before centroids"); return RBP_ERR_STATE; }
@@ -607,6 +735,7 @@ int w1_init_bounds(KmW1* h) {
     RBP_LAUNCHED();
     h->d.pending = 0;
     h->dist_evals += (uint64_t)h->d.n * h->d.k;
+    { const int st = reorder_by_assignment(h); if (st) return st; }
     RBP_CUDA(cudaStreamSynchronize(h->stream));
     h->have_bounds = true;
     return RBP_OK;
@@ -624,10 +753,13 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
     {
-        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 2;  // 2 = 3 blocks/SM, 128-centroid tiles (fastest measured)
+        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 4;  // 4 = 3 blocks/SM, 128-centroid tiles, bounds of 12 centroids ahead prefetched into L2 (fastest measured: profiles/r2y)
         const size_t drift_b = (size_t)d.k * sizeof(float);
         if (variant == 1) elkan_step_kernel<256, 2, kTileK><<<(unsigned)((d.n + 255) / 256), 256, h->smem + drift_b, h->stream>>>(d);
         else if (variant == 2) elkan_step_kernel<128, 3, 128><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
+        else if (variant == 4) elkan_step_kernel<128, 3, 128, false, 12><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
+        else if (variant == 5) elkan_step_kernel<128, 3, 128, false, 24><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
+        else if (variant == 3) elkan_step_kernel<128, 3, 64, true><<<(unsigned)((d.n + 127) / 128), 128, (size_t)2 * 64 * kCdfRow * 4 + drift_b, h->stream>>>(d);
         else elkan_step_kernel<128, 1, kTileK><<<(unsigned)((d.n + 127) / 128), 128, h->smem + drift_b, h->stream>>>(d);
     }
     RBP_LAUNCHED();
@@ -686,8 +818,18 @@ int w1_assign(KmW1* h, uint32_t* assign_out, float* dist_out) {
     assign_kernel<false><<<(unsigned)((h->d.n + kAssignThreads - 1) / kAssignThreads), kAssignThreads, h->smem, h->stream>>>(h->d, h->tmp_assign, h->tmp_dist);
     RBP_LAUNCHED();
     h->dist_evals += (uint64_t)h->d.n * h->d.k;
-    RBP_CUDA(cudaMemcpyAsync(assign_out, h->tmp_assign, h->d.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    if (dist_out) RBP_CUDA(cudaMemcpyAsync(dist_out, h->tmp_dist, h->d.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    const uint32_t* a_src = h->tmp_assign;
+    const float* d_src = h->tmp_dist;
+    if (h->permuted) {  // back to input order (the scratch of the reorder is free between init_bounds calls)
+        const unsigned blocks = (unsigned)((h->d.n + 255) / 256);
+        w1_unpermute_kernel<uint32_t><<<blocks, 256, 0, h->stream>>>(h->tmp_assign, h->perm, h->d.n, h->assign_alt);
+        RBP_LAUNCHED();
+        w1_unpermute_kernel<float><<<blocks, 256, 0, h->stream>>>(h->tmp_dist, h->perm, h->d.n, h->upper_alt);
+        RBP_LAUNCHED();
+        a_src = h->assign_alt; d_src = h->upper_alt;
+    }
+    RBP_CUDA(cudaMemcpyAsync(assign_out, a_src, h->d.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (dist_out) RBP_CUDA(cudaMemcpyAsync(dist_out, d_src, h->d.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RBP_CUDA(cudaStreamSynchronize(h->stream));
     return RBP_OK;
 }
@@ -728,17 +870,27 @@ int w1_bounds(KmW1* h, uint32_t* assign_out, float* upper_out, float* lower_out,
         RBP_LAUNCHED();
         d.pending = 0;
     }
-    if (assign_out) RBP_CUDA(cudaMemcpyAsync(assign_out, d.assign, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (upper_out) RBP_CUDA(cudaMemcpyAsync(upper_out, d.upper, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (stale_out) RBP_CUDA(cudaMemcpyAsync(stale_out, d.stale, d.n, cudaMemcpyDeviceToHost, h->stream));
-    if (lower_out) {  // device layout is [K][N]; the reference's Bounds is per point: transpose on the host
-        std::vector<float> kn((size_t)d.k * d.n);
-        RBP_CUDA(cudaMemcpyAsync(kn.data(), d.lower, kn.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-        RBP_CUDA(cudaStreamSynchronize(h->stream));
-        for (int64_t i = 0; i < d.n; ++i)
-            for (int j = 0; j < d.k; ++j) lower_out[(size_t)i * d.k + j] = kn[(size_t)j * d.n + i];
+    std::vector<uint32_t> perm;
+    if (h->permuted) {
+        perm.resize(d.n);
+        RBP_CUDA(cudaMemcpyAsync(perm.data(), h->perm, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
+    std::vector<uint32_t> a(assign_out ? d.n : 0);
+    std::vector<float> u(upper_out ? d.n : 0);
+    std::vector<uint8_t> sflag(stale_out ? d.n : 0);
+    if (assign_out) RBP_CUDA(cudaMemcpyAsync(a.data(), d.assign, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (upper_out) RBP_CUDA(cudaMemcpyAsync(u.data(), d.upper, d.n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (stale_out) RBP_CUDA(cudaMemcpyAsync(sflag.data(), d.stale, d.n, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<float> kn(lower_out ? (size_t)d.k * d.n : 0);
+    if (lower_out) RBP_CUDA(cudaMemcpyAsync(kn.data(), d.lower, kn.size() * 4, cudaMemcpyDeviceToHost, h->stream));  // device layout is [K][N]; the reference's Bounds is per point
     RBP_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t p = 0; p < d.n; ++p) {  // position p holds input point perm[p]
+        const int64_t i = h->permuted ? (int64_t)perm[p] : p;
+        if (assign_out) assign_out[i] = a[p];
+        if (upper_out) upper_out[i] = u[p];
+        if (stale_out) stale_out[i] = sflag[p];
+        if (lower_out) for (int j = 0; j < d.k; ++j) lower_out[(size_t)i * d.k + j] = kn[(size_t)j * d.n + p];
+    }
     return RBP_OK;
 }
 
