@@ -238,12 +238,22 @@ __device__ __forceinline__ void tile_wait(uint64_t* bar, uint32_t parity) {
 }
 // PIPE: the centroid CDF tiles arrive by TMA bulk copies into a two-stage shared-memory ring (tile t + 1 is in flight while tile t is
 // worked on); otherwise every tile is staged with plain loads between two block barriers.
-template <int THREADS, int MINB, int TILE, bool PIPE = false, int kFar = 0>
+// kRing > 0: the bounds stream lower[j][i] is fetched by per-thread cp.async copies kRing groups (of 4 centroids) ahead into a private
+// shared-memory ring.  With the one-group register lookahead a warp had 4 x 128 B in flight and an SM (12 warps at 180 registers) about
+// 6 KB — by Little's law ~1.1 TB/s over the whole device at HBM latency, which is what the step measured (profiles/r2y, r2z).
+// kFast (needs kRing): groups of 4 centroids that are complete, in blocks whose threads all own a point, take a path without the
+// per-member tail / liveness tests, with running pointers instead of 64-bit index products and with the member-by-member walk only in
+// warps where some lane examines a centroid — bookkeeping was 57 % of the step's instructions (profiles/r2ab_elkan_step_hot_lines.txt).
+template <int THREADS, int MINB, int TILE, bool PIPE = false, int kFar = 0, int kRing = 0, bool kFast = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 elkan_step_kernel(KmDev km) {
+    static_assert(!kFast || kRing > 0, "the fast path reads the bounds from the ring");
     extern __shared__ __align__(128) float s_cdf[];
     __shared__ __align__(8) uint64_t s_bar[2];
+    static_assert(TILE % 4 == 0, "a group of 4 centroids never straddles two tiles");
     float* s_drift = s_cdf + (PIPE ? (size_t)2 * TILE : (size_t)min(km.k, TILE)) * kCdfRow;  // [K] drift of the previous step
+    constexpr int kSlots = kRing == 6 ? 8 : kRing + 2;     // the slot being refilled was read (at least) two groups ago
+    float* s_ring = s_drift + ((km.k + 3) & ~3);            // [kSlots][4][THREADS], cell (slot, g, thread) is private to the thread
     for (int j = threadIdx.x; j < km.k; j += blockDim.x) s_drift[j] = km.pending ? km.drift[j] : 0.0f;
     if (PIPE && threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[b])));
@@ -260,6 +270,24 @@ elkan_step_kernel(KmDev km) {
 #pragma unroll
         for (int b = 0; b < kBins; ++b) X[b] = 0.0f;
     }
+    const int n_groups = (km.k + 3) >> 2;
+    auto ring_issue = [&](int G) {  // one commit group per group of centroids, also when there is nothing to fetch: the wait below counts groups
+        if (kRing > 0) {
+            if (G < n_groups && live) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int j = G * 4 + g;
+                    if (j < km.k) {
+                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_ring + ((size_t)(G % kSlots) * 4 + g) * THREADS + threadIdx.x);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(km.lower + (size_t)j * km.n + i) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    if (kRing > 0)
+        for (int G = 0; G < kRing; ++G) ring_issue(G);
     uint32_t c = 0, c_prior = 0;
     float u = 0.0f;
     bool stale = false;
@@ -284,6 +312,11 @@ elkan_step_kernel(KmDev km) {
         }
     }
     const uint32_t c_refresh = c;
+    const bool block_full = (int64_t)(blockIdx.x + 1) * THREADS <= km.n;
+    const int n_full_groups = km.k >> 2;
+    const size_t n4 = 4 * (size_t)km.n;
+    float* lower_ptr = km.lower + i;                      // &lower[j][i] of the group being worked on
+    const float* prow = km.pair + (size_t)c * km.kp;      // the pairwise row of the current centroid
     for (int j0 = 0; j0 < km.k; j0 += TILE) {
         const int kt = min(TILE, km.k - j0);
         float* tile = s_cdf;
@@ -306,13 +339,67 @@ elkan_step_kernel(KmDev km) {
         uint32_t c_pref = c;
         auto prefetch = [&](int jj) {
             const int g_n = min(4, kt - jj);
+            if (kRing == 0) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) ln[g] = (g < g_n && live) ? km.lower[(size_t)(j0 + jj + g) * km.n + i] : 0.0f;
+                for (int g = 0; g < 4; ++g) ln[g] = (g < g_n && live) ? km.lower[(size_t)(j0 + jj + g) * km.n + i] : 0.0f;
+            }
             prn = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);
             c_pref = c;
         };
         prefetch(0);
-        for (int jj = 0; jj < kt; jj += 4) {
+        for (int jj = 0; jj < kt; jj += 4, lower_ptr += n4) {
+            if (kFast && block_full && jj + 4 <= kt) {
+                const int jg = j0 + jj, G = jg >> 2;
+                if (G + kRing < n_full_groups) {  // fetch group G + kRing: 4 complete rows of the bounds stream
+                    const float* src = lower_ptr + (size_t)kRing * n4;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)((G + kRing) % kSlots) * 4 * THREADS + threadIdx.x);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(g * THREADS * 4)), "l"(src + (size_t)g * km.n) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                } else ring_issue(G + kRing);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kRing) : "memory");
+                const float* cell = s_ring + (size_t)(G % kSlots) * 4 * THREADS + threadIdx.x;
+                float l[4] = {cell[0], cell[THREADS], cell[2 * THREADS], cell[3 * THREADS]};
+                float4 pr = prn;
+                if (c_pref != c) pr = *reinterpret_cast<const float4*>(prow + jg);  // reassigned since the prefetch
+                if (jj + 4 < kt) { prn = *reinterpret_cast<const float4*>(prow + jg + 4); c_pref = c; }
+                const float4 dr = *reinterpret_cast<const float4*>(s_drift + jg);    // zeros on the first step: (l - 0).max(0) = l for l >= +0
+                l[0] = l[0] - dr.x; l[0] = l[0] > 0.0f ? l[0] : 0.0f;
+                l[1] = l[1] - dr.y; l[1] = l[1] > 0.0f ? l[1] : 0.0f;
+                l[2] = l[2] - dr.z; l[2] = l[2] > 0.0f ? l[2] : 0.0f;
+                l[3] = l[3] - dr.w; l[3] = l[3] > 0.0f ? l[3] : 0.0f;
+                if (refreshed && (c_refresh >> 2) == (uint32_t)G) {  // Bounds::refresh sets lower[j]
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) if ((c_refresh & 3u) == (uint32_t)g) l[g] = refreshed_d;
+                }
+                float half[4] = {0.5f * pr.x, 0.5f * pr.y, 0.5f * pr.z, 0.5f * pr.w};
+                const uint32_t cg = c - (uint32_t)jg;  // the current centroid's place in the group (>= 4: not in it)
+                const bool want = act && ((cg != 0u && u > l[0] && u > half[0]) || (cg != 1u && u > l[1] && u > half[1]) ||
+                                          (cg != 2u && u > l[2] && u > half[2]) || (cg != 3u && u > l[3] && u > half[3]));
+                if (__any_sync(0xFFFFFFFFu, want)) {
+                    float d[4];
+                    dist_group<4>(X, tile + (size_t)jj * kCdfRow, d);
+                    if (want) {
+                        uint32_t c_row = c;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t j = (uint32_t)(jg + g);
+                            if (c != c_row) {  // the pairwise row switches when the point is reassigned mid-group
+                                const float4 p2 = *reinterpret_cast<const float4*>(prow + jg);
+                                half[0] = 0.5f * p2.x; half[1] = 0.5f * p2.y; half[2] = 0.5f * p2.z; half[3] = 0.5f * p2.w;
+                                c_row = c;
+                            }
+                            if (j != c && u > l[g] && u > half[g]) {  // bounds.rs:57-61 has_shifted
+                                l[g] = d[g];                           // witness (bounds.rs:81-87)
+                                if (d[g] < u) { c = j; u = d[g]; prow = km.pair + (size_t)c * km.kp; }
+                            }
+                        }
+                    }
+                }
+                lower_ptr[0] = l[0]; lower_ptr[(size_t)km.n] = l[1]; lower_ptr[2 * (size_t)km.n] = l[2]; lower_ptr[3 * (size_t)km.n] = l[3];
+                continue;
+            }
             const int g_n = min(4, kt - jj);
             float l[4], half[4];
             bool want = false;
@@ -320,8 +407,16 @@ elkan_step_kernel(KmDev km) {
             float4 pr = prn;
             if (c_pref != c) pr = *reinterpret_cast<const float4*>(km.pair + (size_t)c * km.kp + j0 + jj);  // reassigned since the prefetch
             half[0] = 0.5f * pr.x; half[1] = 0.5f * pr.y; half[2] = 0.5f * pr.z; half[3] = 0.5f * pr.w;
+            if (kRing > 0) {
+                const int G = (j0 + jj) >> 2;
+                ring_issue(G + kRing);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kRing) : "memory");  // all but the kRing newest groups have landed: group G is in its slot
 #pragma unroll
-            for (int g = 0; g < 4; ++g) l[g] = ln[g];
+                for (int g = 0; g < 4; ++g) l[g] = (g < g_n && live) ? s_ring[((size_t)(G % kSlots) * 4 + g) * THREADS + threadIdx.x] : 0.0f;
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) l[g] = ln[g];
+            }
             if (jj + 4 < kt) prefetch(jj + 4);
             if (kFar > 0 && live && j0 + jj + kFar + 4 <= km.k) {  // pull the bounds of a later group from HBM into L2 (they cross tiles: the stream is [K][N])
 #pragma unroll
@@ -344,7 +439,7 @@ elkan_step_kernel(KmDev km) {
             // four distances are produced together.
             float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (__any_sync(0xFFFFFFFFu, want)) {
-                if (g_n == 4) dist_group<4>(X, tile + (size_t)jj * kCdfRow, d);
+                if (!kFast && g_n == 4) dist_group<4>(X, tile + (size_t)jj * kCdfRow, d);
                 else
                     for (int g = 0; g < g_n; ++g) { float t[1]; dist_group<1>(X, tile + (size_t)(jj + g) * kCdfRow, t); d[g] = t[0]; }
             }
@@ -359,7 +454,7 @@ elkan_step_kernel(KmDev km) {
                     }
                     if (want && act && (uint32_t)j != c && u > l[g] && u > half[g]) {  // bounds.rs:57-61 has_shifted
                         l[g] = d[g];                                   // witness (bounds.rs:81-87)
-                        if (d[g] < u) { c = (uint32_t)j; u = d[g]; }
+                        if (d[g] < u) { c = (uint32_t)j; u = d[g]; prow = km.pair + (size_t)c * km.kp; }
                     }
                     km.lower[(size_t)j * km.n + i] = l[g];
                 }
@@ -598,6 +693,10 @@ int w1_create(int kind, int64_t n, int k, int bins, const uint8_t* counts, int d
         cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128, false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(elkan_step_kernel<128, 3, 128, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem + (size_t)k * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 96, false, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)96 * kCdfRow * 4 + ((size_t)k + 4) * sizeof(float) + (size_t)10 * 4 * 128 * 4)) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 64, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)64 * kCdfRow * 4 + ((size_t)k + 4) * sizeof(float) + (size_t)18 * 4 * 128 * 4)) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 56, true, 0, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 56 * kCdfRow * 4 + ((size_t)k + 4) * sizeof(float) + (size_t)8 * 4 * 128 * 4)) != cudaSuccess ||
+        cudaFuncSetAttribute(elkan_step_kernel<128, 3, 96, false, 0, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)96 * kCdfRow * 4 + ((size_t)k + 4) * sizeof(float) + (size_t)8 * 4 * 128 * 4)) != cudaSuccess ||
         cudaFuncSetAttribute(elkan_step_kernel<128, 3, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 64 * kCdfRow * 4 + (size_t)k * sizeof(float))) != cudaSuccess ||
         cudaFuncSetAttribute(accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
@@ -753,12 +852,16 @@ int w1_step_local(KmW1* h) {
     RBP_CUDA(cudaMemsetAsync(d.sizes, 0, d.k * sizeof(uint32_t), h->stream));
     RBP_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)d.k * (kBins + 1) * 8, h->stream));
     {
-        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 4;  // 4 = 3 blocks/SM, 128-centroid tiles, bounds of 12 centroids ahead prefetched into L2 (fastest measured: profiles/r2y)
+        static const int variant = getenv("RBP_STEP_VARIANT") ? atoi(getenv("RBP_STEP_VARIANT")) : 8;  // 8 = 3 blocks/SM, TMA double-buffered 56-centroid tiles, bounds 6 groups ahead in a cp.async ring, fast path for complete groups (fastest measured: profiles/r2ac)
         const size_t drift_b = (size_t)d.k * sizeof(float);
         if (variant == 1) elkan_step_kernel<256, 2, kTileK><<<(unsigned)((d.n + 255) / 256), 256, h->smem + drift_b, h->stream>>>(d);
         else if (variant == 2) elkan_step_kernel<128, 3, 128><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
         else if (variant == 4) elkan_step_kernel<128, 3, 128, false, 12><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
         else if (variant == 5) elkan_step_kernel<128, 3, 128, false, 24><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 128) * kCdfRow * 4 + drift_b, h->stream>>>(d);
+        else if (variant == 6) elkan_step_kernel<128, 3, 96, false, 0, 8><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 96) * kCdfRow * 4 + ((d.k + 3) & ~3) * sizeof(float) + (size_t)10 * 4 * 128 * 4, h->stream>>>(d);
+        else if (variant == 7) elkan_step_kernel<128, 3, 64, false, 0, 16><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 64) * kCdfRow * 4 + ((d.k + 3) & ~3) * sizeof(float) + (size_t)18 * 4 * 128 * 4, h->stream>>>(d);
+        else if (variant == 8) elkan_step_kernel<128, 3, 56, true, 0, 6, true><<<(unsigned)((d.n + 127) / 128), 128, (size_t)2 * 56 * kCdfRow * 4 + ((d.k + 3) & ~3) * sizeof(float) + (size_t)8 * 4 * 128 * 4, h->stream>>>(d);
+        else if (variant == 9) elkan_step_kernel<128, 3, 96, false, 0, 6, true><<<(unsigned)((d.n + 127) / 128), 128, (size_t)std::min(d.k, 96) * kCdfRow * 4 + ((d.k + 3) & ~3) * sizeof(float) + (size_t)8 * 4 * 128 * 4, h->stream>>>(d);
         else if (variant == 3) elkan_step_kernel<128, 3, 64, true><<<(unsigned)((d.n + 127) / 128), 128, (size_t)2 * 64 * kCdfRow * 4 + drift_b, h->stream>>>(d);
         else elkan_step_kernel<128, 1, kTileK><<<(unsigned)((d.n + 127) / 128), 128, h->smem + drift_b, h->stream>>>(d);
     }

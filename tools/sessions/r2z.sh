@@ -2,7 +2,7 @@
 # r2z: Elkan step with the points stored sorted by their first assignment (RBP_W1_REORDER, default on) against input order
 O=gpurun_out
 TAG=${1:-r2z}
-timeout 900 python -m pytest tests/test_lloyd_gpu.py tests/test_distributed_gpu.py -x -q -m gpu --timeout 300 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_lloyd_gpu.py -x -q -m gpu --timeout 300 2>&1 | tail -3
 for R in 0 1; do for K in 100 500; do
 RBP_W1_REORDER=$R timeout 400 python bench.py --workload lloyd_turn --k $K --points 6000000 --steps 8 --warmup 3 --skip-cpu-baseline > $O/bench_${TAG}_r${R}_k$K.json 2> $O/bench_${TAG}_r${R}_k$K.err; tail -1 $O/bench_${TAG}_r${R}_k$K.err
 python - $O/bench_${TAG}_r${R}_k$K.json $R $K <<'PY'
