@@ -43,6 +43,28 @@ def test_full_pipeline_bit_exact(rbp, oracle, n, k, seed):
     assert f32eq(g.metric(), o.metric())
 
 
+def test_reseeding_after_bounds_sees_the_points_in_input_order(rbp, oracle):
+    # init_bounds stores the points sorted by their first assignment (coherent warps in the Elkan step); k-means++ draws by a prefix
+    # sum over the points in INPUT order, so a second initialisation on the same layer must undo that storage order first
+    pts = turn_histograms(6000, seed=11)
+    g = rbp.lloyd.Layer(pts, 24)
+    o = oracle.OracleKmeans(pts, 24, threads=8)
+    g.init_centroids(5); o.init_centroids(5)
+    g.init_bounds(); o.init_bounds()
+    for _ in range(2):
+        g.step(); o.step()
+    assert np.array_equal(g.lookup(), o.lookup())                                    # per-point output, input order
+    assert np.array_equal(g.init_centroids(6), o.init_centroids(6))                  # re-seeded on the reordered layer
+    g.init_bounds(); o.init_bounds()                                                 # second reorder composes with nothing stale
+    for it in range(3):
+        s = g.step()
+        drift, sizes, re = o.step()
+        assert f32eq(s.drift, drift) and np.array_equal(s.sizes, sizes) and s.reassignment == re, it
+    ga, gu, gl, gs = g.bounds(True)
+    oa, ou, ol, os_ = o.bounds(True)
+    assert np.array_equal(ga, oa) and f32eq(gu, ou) and f32eq(gl, ol) and np.array_equal(gs, os_)
+
+
 def test_explicit_centroids_and_tiny_k(rbp, oracle):
     pts = turn_histograms(300, seed=9)
     g = rbp.lloyd.Layer(pts, 1)
