@@ -473,6 +473,11 @@ elkan_step_kernel(KmDev km) {
 // ── recompute (elkan.rs:125-142): integer merge of member points into the new centroids ──
 // Each block privatises the K x 102 (bins + weight) u32 accumulators in shared memory over a contiguous slice of
 // points, then flushes non-zero cells with 64-bit global atomics: integer addition, so any order is exact.
+// A warp walks 32 consecutive points.  Stored sorted by their first assignment (reorder_by_assignment), most of a warp's points belong to
+// one cluster, and 32 lanes adding to the same (cluster, bin) cell is a 32-way shared-memory atomic conflict: 1.3 ms of a 4.3 ms iteration
+// at 3 M points x k = 100 (profiles/r2ae_lloyd_k100_launches.csv).  So the warp first sums the counts of its LARGEST group of lanes that
+// share a cluster (two REDUX per word of 4 bins: bytes widened to 16-bit pairs, 32 x 255 < 2^16) and four lanes add the sums; the other
+// lanes (points that have moved since the reorder) add their own counts.  Integer sums: exact in any grouping.
 template <bool SMEM>
 __global__ void __launch_bounds__(256)
 accumulate_kernel(KmDev km, int64_t per_block) {
@@ -482,27 +487,68 @@ accumulate_kernel(KmDev km, int64_t per_block) {
         for (int t = threadIdx.x; t < cells; t += blockDim.x) s_acc[t] = 0u;
         __syncthreads();
     }
+    auto add_cell = [&](uint32_t c, int b, uint32_t v) {
+        if (SMEM) atomicAdd(&s_acc[c * (kBins + 1) + b], v);
+        else atomicAdd(km.acc + (size_t)c * (kBins + 1) + b, (unsigned long long)v);
+    };
+    const int lane = threadIdx.x & 31;
     const int64_t lo = blockIdx.x * per_block, hi = min(km.n, lo + per_block);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const uint32_t c = km.assign[i];
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(km.pts + (size_t)i * kRow);
-        uint32_t w = 0;
-        for (int q = 0; q < kRow / 4; ++q) {
-            const uint32_t v = row[q];
-            if (!v) continue;
-            for (int t = 0; t < 4; ++t) {
-                const uint32_t cnt = (v >> (8 * t)) & 0xFFu;
-                const int b = 4 * q + t;
-                if (cnt && b < kBins) {
-                    if (SMEM) atomicAdd(&s_acc[c * (kBins + 1) + b], cnt);
-                    else atomicAdd(km.acc + (size_t)c * (kBins + 1) + b, (unsigned long long)cnt);
-                    w += cnt;
-                }
+    for (int64_t base = lo + (threadIdx.x - lane); base < hi; base += blockDim.x) {
+        const int64_t i = base + lane;
+        const bool live = i < hi;
+        const uint32_t c = live ? km.assign[i] : 0xFFFFFFFFu;
+        uint32_t word[kRow / 4];                                       // the point's 112 bytes, loaded once
+        {
+            const uint4* row4 = reinterpret_cast<const uint4*>(km.pts + (size_t)(live ? i : base) * kRow);
+#pragma unroll
+            for (int q4 = 0; q4 < kRow / 16; ++q4) {
+                const uint4 v4 = live ? row4[q4] : make_uint4(0u, 0u, 0u, 0u);
+                word[4 * q4] = v4.x; word[4 * q4 + 1] = v4.y; word[4 * q4 + 2] = v4.z; word[4 * q4 + 3] = v4.w;
             }
         }
-        if (SMEM) atomicAdd(&s_acc[c * (kBins + 1) + kBins], w);
-        else atomicAdd(km.acc + (size_t)c * (kBins + 1) + kBins, (unsigned long long)w);
-        atomicAdd(km.sizes + c, 1u);
+        // the largest group of lanes with one cluster; if the dead lanes of a tail warp (they share 0xFFFFFFFF) outnumber every live
+        // group, there is no leader and every live lane takes the per-lane path
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, c);
+        const uint32_t most = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)__popc(same));
+        const uint32_t leaders = __ballot_sync(0xFFFFFFFFu, live && (uint32_t)__popc(same) == most);
+        uint32_t grp = 0u, c0 = 0u;
+        if (leaders) { const int lead = __ffs(leaders) - 1; grp = __shfl_sync(0xFFFFFFFFu, same, lead); c0 = __shfl_sync(0xFFFFFFFFu, c, lead); }
+        const bool in = grp >> lane & 1u;
+        if (__popc(grp) >= 4) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int q = 0; q < kRow / 4; ++q) {                       // bins 4q .. 4q+3
+                const int valid = kBins - 4 * q;                       // how many of them exist (the row is padded to 112 bytes)
+                if (valid <= 0) continue;
+                uint32_t v = in ? word[q] : 0u;
+                if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+                if (!__any_sync(0xFFFFFFFFu, v != 0u)) continue;
+                const uint32_t even = __reduce_add_sync(0xFFFFFFFFu, v & 0x00FF00FFu);          // bins 4q (low half) and 4q+2 (high half)
+                const uint32_t odd = __reduce_add_sync(0xFFFFFFFFu, (v >> 8) & 0x00FF00FFu);    // bins 4q+1 and 4q+3
+                const uint32_t sum = lane == 0 ? (even & 0xFFFFu) : lane == 1 ? (odd & 0xFFFFu) : lane == 2 ? (even >> 16) : (odd >> 16);
+                if (lane < 4 && lane < valid && sum) add_cell(c0, 4 * q + lane, sum);
+                w += (even & 0xFFFFu) + (odd & 0xFFFFu) + (even >> 16) + (odd >> 16);
+            }
+            if (lane == 0) {
+                add_cell(c0, kBins, w);
+                atomicAdd(km.sizes + c0, (unsigned int)__popc(grp));
+            }
+        } else grp = 0u;
+        if (live && !(grp >> lane & 1u)) {  // everyone else: per-lane atomics
+            uint32_t w = 0;
+#pragma unroll
+            for (int q = 0; q < kRow / 4; ++q) {
+                const uint32_t v = word[q];
+                if (!v) continue;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t cnt = (v >> (8 * t)) & 0xFFu;
+                    if (cnt && 4 * q + t < kBins) { add_cell(c, 4 * q + t, cnt); w += cnt; }
+                }
+            }
+            add_cell(c, kBins, w);
+            atomicAdd(km.sizes + c, 1u);
+        }
     }
     if (SMEM) {
         __syncthreads();
