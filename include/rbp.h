@@ -138,6 +138,40 @@ int rbp_profile_averaged(rbp_solver_t* s, uint32_t info_key, float* probs, int c
  * [4] max nodes of a sampled tree, [5] max walker infosets per sampled tree */
 int rbp_solver_game_shape(rbp_solver_t* s, int out[6]);
 
+/* ---- safe subgame solving on the small games: `WorldSolver` (crates/subgame/src/world/solver.rs:33-146), which is also
+ * `SubGameSolver` without an origin (crates/subgame/src/solver.rs:46-146; depth-limited frontiers are NOT built) ----
+ * RNG contract (the reference samples the world from the unseeded thread RNG): world = weighted(belief weights) on
+ * Philox counter (step, 0, 0xFFFFFFFE, tag 5); the step's tree draws with tree_id = world. */
+typedef struct rbp_subgame rbp_subgame_t;
+/* `Partition::partition::<W>` (world/partition.rs:27-53): posterior reach of every secret (ascending secret order) -> its world
+ * (0 = highest reach) and the probability mass of every world */
+int rbp_subgame_partition(const float* reach, int n_secrets, int worlds, int32_t* world_of_secret, float* weights);
+/* `WorldSolver::new(encoder, profile, external, belief, recall)`: `blueprint` = a trained Kuhn / Leduc solver (its table is copied: the
+ * blueprint may be destroyed afterwards); belief = world of every rank (NULL = `Belief` without members: every secret is remembered)
+ * + `worlds` weights; recall = the observed deal (c0, c1: card = 2 * rank + suit, `Card::ALL` order) and the path of branch indices
+ * (`branches()` order; at a chance node: index among the cards still in the deck) from the dealt root to the entry state.
+ * RBP_ERR_INVALID if a chance node is reachable from the entry state (that needs the frontier machinery). */
+int rbp_subgame_create(rbp_solver_t* blueprint, int external, int worlds, const int32_t* world_of_rank /* [3] or NULL */, const float* weights,
+                       int c0, int c1, const uint8_t* path, int path_len, uint64_t seed, rbp_subgame_t** out);
+void rbp_subgame_destroy(rbp_subgame_t* g);
+/* host half of the constructor (no device needed): per world the restricted deal [8][2], the flat node and the infoset key of the entry state */
+int rbp_subgame_entries(int game, int external, int worlds, const int32_t* world_of_rank, int c0, int c1, const uint8_t* path, int path_len,
+                        int32_t* cards16, int32_t* nodes8, uint32_t* info_keys8);
+/* `WorldSolver::step` x n (world/solver.rs:118-146): sample a world, `WorldRestrict::restrict` (kuhn/src/encoder.rs:47-66,
+ * leduc/src/encoder.rs:48-70), one ExternalSampling tree, SummedRegret + LinearWeight fold into the world's table */
+int rbp_subgame_step(rbp_subgame_t* g, uint64_t n);
+/* `Solver::spend` (mccfr/src/solver/solver.rs:130-137) */
+int rbp_subgame_spend(rbp_subgame_t* g, double seconds, uint64_t* steps_out, double* elapsed_out);
+/* steps run (`WorldProfile::t`), how often each world was drawn [8], the restricted entry deal of each world [8][2] */
+int rbp_subgame_info(rbp_subgame_t* g, uint64_t* steps, uint64_t* drawn8, int32_t* entry_cards16);
+/* `WorldProfile::local` of one world (world/profile.rs:25-36): the rows the subgame wrote, sorted by (info_key, action) */
+int rbp_subgame_export(rbp_subgame_t* g, int world, rbp_profile_row_t* rows, int cap, int* n_out);
+/* `CfrNash::averaged_policy` over `WorldInfo(world, info)`: local weights, the blueprint's where the edge was never written */
+int rbp_subgame_averaged(rbp_subgame_t* g, int world, uint32_t info_key, float* probs, int cap, int* n_out);
+/* `Harvest::harvest(base)` (world/solver.rs:148-191): refined policy (mean over the worlds of the regret-matching policy), visits
+ * summed over the worlds, positive regret summed over edges and worlds */
+int rbp_subgame_harvest(rbp_subgame_t* g, uint32_t info_key, float* refined, uint32_t* visits, float* regret, int cap, int* n_out);
+
 /* Multi-GPU exchange (one process per GPU).  The library does not link a collective library: the host
  * (Rust shim / torch.distributed) moves these device buffers with NCCL.  BATCHED fold: after
  * rbp_solver_sample() each rank holds its blocked partial sums; all-gather `delta` buffers across ranks into

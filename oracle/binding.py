@@ -130,6 +130,97 @@ class OracleSolver:
         return [out[i] for i in range(n)]
 
 
+def _sub():
+    l = lib()
+    if not getattr(l, "_sub_ready", False):
+        vp, u64, i32, u32, f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_float
+        l.orc_partition.argtypes = [vp, i32, i32, vp, vp]
+        l.orc_subgame_create.restype = vp
+        l.orc_subgame_create.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, i32, u64]
+        l.orc_subgame_destroy.argtypes = [vp]
+        l.orc_subgame_step.argtypes = [vp, u64]
+        l.orc_subgame_t.restype = u64
+        l.orc_subgame_t.argtypes = [vp]
+        l.orc_subgame_drawn.argtypes = [vp, vp]
+        l.orc_subgame_sum_regret.restype = f32
+        l.orc_subgame_sum_regret.argtypes = [vp]
+        l.orc_subgame_entry.argtypes = [vp, i32, vp]
+        l.orc_subgame_entry_key.restype = u32
+        l.orc_subgame_entry_key.argtypes = [vp, i32]
+        l.orc_subgame_export.argtypes = [vp, i32, vp, i32]
+        l.orc_subgame_averaged.argtypes = [vp, i32, u32, vp]
+        l.orc_subgame_harvest.argtypes = [vp, u32, vp, vp, vp]
+        l._sub_ready = True
+    return l
+
+
+def partition(reach, worlds):
+    """`Partition::partition::<W>` (subgame/src/world/partition.rs:27-53): (world of every secret, per-world weights)."""
+    reach = np.ascontiguousarray(reach, dtype=np.float32)
+    world_of, weights = np.zeros(len(reach), np.int32), np.zeros(worlds, np.float32)
+    _sub().orc_partition(reach.ctypes.data, len(reach), worlds, world_of.ctypes.data, weights.ctypes.data)
+    return world_of, weights
+
+
+class OracleSubgame:
+    """`WorldSolver` / `SubGameSolver` without an origin over an OracleSolver blueprint (oracle/subgame.hpp)."""
+
+    def __init__(self, blueprint, external, world_of_rank, weights, cards, path=(), seed=0):
+        self.blueprint = blueprint  # keeps the blueprint alive: the subgame reads through to it
+        self.worlds = len(weights)
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        m = None if world_of_rank is None else np.ascontiguousarray(world_of_rank, dtype=np.int32)
+        p = np.ascontiguousarray(list(path), dtype=np.uint8)
+        self._h = _sub().orc_subgame_create(blueprint._h, external, self.worlds, None if m is None else m.ctypes.data, w.ctypes.data,
+                                            cards[0], cards[1], p.ctypes.data if len(p) else None, len(p), seed)
+        if not self._h:
+            raise ValueError("orc_subgame_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _sub().orc_subgame_destroy(self._h)
+            self._h = None
+
+    def step(self, n=1):
+        _sub().orc_subgame_step(self._h, n)
+        return self
+
+    @property
+    def t(self):
+        return _sub().orc_subgame_t(self._h)
+
+    def drawn(self):
+        out = np.zeros(self.worlds, np.uint64)
+        _sub().orc_subgame_drawn(self._h, out.ctypes.data)
+        return out
+
+    def sum_regret(self):
+        return _sub().orc_subgame_sum_regret(self._h)
+
+    def entry(self, world):
+        out = np.zeros(2, np.int32)
+        _sub().orc_subgame_entry(self._h, world, out.ctypes.data)
+        return int(out[0]), int(out[1])
+
+    def entry_key(self, world):
+        return int(_sub().orc_subgame_entry_key(self._h, world))
+
+    def profile_rows(self, world):
+        buf = np.zeros(4096, dtype=ROW_DTYPE)
+        n = _sub().orc_subgame_export(self._h, world, buf.ctypes.data, len(buf))
+        return buf[:n]
+
+    def averaged_distribution(self, world, info_key):
+        out = np.zeros(8, np.float32)
+        n = _sub().orc_subgame_averaged(self._h, world, info_key, out.ctypes.data)
+        return out[:n]
+
+    def harvest(self, info_key):
+        refined, visits, regret = np.zeros(4, np.float32), np.zeros(4, np.uint32), np.zeros(1, np.float32)
+        n = _sub().orc_subgame_harvest(self._h, info_key, refined.ctypes.data, visits.ctypes.data, regret.ctypes.data)
+        return refined[:n], visits[:n], float(regret[0])
+
+
 def _deuce():
     l = lib()
     if not getattr(l, "_deuce_ready", False):

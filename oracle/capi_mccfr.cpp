@@ -4,6 +4,7 @@
 #include <cstdio>
 
 #include "mccfr.hpp"
+#include "subgame.hpp"
 
 using namespace orc;
 
@@ -120,6 +121,104 @@ int orc_solver_averaged(OrcSolver* s, uint32_t info_key, float* out) {
         auto v = sv.averaged(info_key);
         for (int a = 0; a < v.n; ++a) out[a] = v.p[a];
         return v.n;
+    });
+}
+
+}  // extern "C"
+
+// ── safe subgame solving on the small games (oracle/subgame.hpp) ──
+struct OrcSubgame {
+    int game;
+    SubSolver<KuhnGame>* kuhn = nullptr;
+    SubSolver<LeducGame>* leduc = nullptr;
+    ~OrcSubgame() { delete kuhn; delete leduc; }
+};
+template <class G>
+static typename G::State entry_state(typename G::State s, const uint8_t* path, int n) {
+    for (int i = 0; i < n; ++i) {  // path = branch indices in `branches()` order
+        uint8_t ed[MAX_BRANCH];
+        const int k = G::branches(s, ed);
+        if (path[i] >= k) break;
+        s = G::apply(s, ed[path[i]]);
+    }
+    return s;
+}
+template <class F>
+static auto with_sub(OrcSubgame* g, F f) { return g->game == 0 ? f(*g->kuhn) : f(*g->leduc); }
+
+extern "C" {
+void orc_partition(const float* reach, int n, int worlds, int32_t* world_of, float* weights) { partition(reach, n, worlds, world_of, weights); }
+OrcSubgame* orc_subgame_create(OrcSolver* bp, int external, int worlds, const int32_t* world_of_rank, const float* weights, int c0, int c1,
+                               const uint8_t* path, int path_len, uint64_t seed) {
+    if (!bp || bp->game > 1 || worlds < 1 || worlds > MAX_WORLDS) return nullptr;
+    OrcSubgame* g = new OrcSubgame();
+    g->game = bp->game;
+    if (bp->game == 0) {
+        KuhnGame::State root{{(uint8_t)c0, (uint8_t)c1}, KuhnGame::Open};
+        g->kuhn = new SubSolver<KuhnGame>(&bp->kuhn, external, worlds, world_of_rank, weights, entry_state<KuhnGame>(root, path, path_len), seed);
+    } else {
+        LeducGame::State root{{(uint8_t)c0, (uint8_t)c1}, LeducGame::R1, 0, LeducGame::SOpen, 0, 0};
+        g->leduc = new SubSolver<LeducGame>(&bp->leduc, external, worlds, world_of_rank, weights, entry_state<LeducGame>(root, path, path_len), seed);
+    }
+    return g;
+}
+void orc_subgame_destroy(OrcSubgame* g) { delete g; }
+void orc_subgame_step(OrcSubgame* g, uint64_t n) { with_sub(g, [&](auto& sv) { for (uint64_t i = 0; i < n; ++i) sv.step(); return 0; }); }
+uint64_t orc_subgame_t(OrcSubgame* g) { return with_sub(g, [](auto& sv) { return sv.t; }); }
+void orc_subgame_drawn(OrcSubgame* g, uint64_t* out) { with_sub(g, [&](auto& sv) { for (int w = 0; w < sv.worlds; ++w) out[w] = sv.drawn[w]; return 0; }); }
+float orc_subgame_sum_regret(OrcSubgame* g) { return with_sub(g, [](auto& sv) { return sv.sum_regret(); }); }
+void orc_subgame_entry(OrcSubgame* g, int world, int* cards2) {
+    with_sub(g, [&](auto& sv) { auto s = sv.restrict(world); cards2[0] = s.hole[0]; cards2[1] = s.hole[1]; return 0; });
+}
+uint32_t orc_subgame_entry_key(OrcSubgame* g, int world) {
+    return with_sub(g, [&](auto& sv) { using GG = typename std::decay_t<decltype(sv)>::Game; return (uint32_t)GG::info_key(sv.restrict(world)); });
+}
+// rows of one world that exist locally, sorted by (info_key, action)
+int orc_subgame_export(OrcSubgame* g, int world, OrcRow* out, int cap) {
+    return with_sub(g, [&](auto& sv) {
+        std::vector<OrcRow> rows;
+        for (auto& kv : sv.local[world].profile.rows)
+            for (int a = 0; a < kv.second.n; ++a)
+                if (kv.second.present[a]) {
+                    const Encounter& e = kv.second.e[a];
+                    rows.push_back(OrcRow{kv.first, (uint32_t)a, e.weight, e.regret, e.payoff, e.visits});
+                }
+        std::sort(rows.begin(), rows.end(), [](const OrcRow& x, const OrcRow& y) { return x.info_key != y.info_key ? x.info_key < y.info_key : x.action < y.action; });
+        const int n = (int)rows.size();
+        for (int i = 0; i < n && i < cap; ++i) out[i] = rows[i];
+        return n;
+    });
+}
+// CfrNash::averaged_policy over WorldInfo(world, info): local weights, the blueprint's (floored) where the edge was never written
+int orc_subgame_averaged(OrcSubgame* g, int world, uint32_t info_key, float* out) {
+    return with_sub(g, [&](auto& sv) {
+        auto v = sv.local[world].averaged(info_key);
+        for (int a = 0; a < v.n; ++a) out[a] = v.p[a];
+        return v.n;
+    });
+}
+// Harvest (world/solver.rs:148-191) at a base infoset: refined[a] = sum over worlds of iterated policy / W, visits[a] = sum of cum_visits,
+// regret = sum over edges and worlds of max(cum_regret, 0)
+int orc_subgame_harvest(OrcSubgame* g, uint32_t info_key, float* refined, uint32_t* visits, float* regret) {
+    return with_sub(g, [&](auto& sv) {
+        int n = 0;
+        float reg = 0.0f;
+        for (int a = 0; a < MAXA; ++a) { refined[a] = 0.0f; visits[a] = 0u; }
+        for (int w = 0; w < sv.worlds; ++w) {
+            InfoView v = view_of(sv.local[w].profile, info_key);
+            n = v.n;
+            for (int a = 0; a < v.n; ++a) refined[a] += v.r[a] / v.rd / (float)sv.worlds;
+        }
+        for (int a = 0; a < n; ++a)
+            for (int w = 0; w < sv.worlds; ++w) visits[a] += sv.local[w].profile.cum_visits(info_key, a);
+        const InfoView v0 = view_of(sv.local[0].profile, info_key);
+        for (int a = 0; a < n; ++a)
+            for (int w = 0; w < sv.worlds; ++w) {
+                const float r = sv.local[w].profile.cum_regret(info_key, a, v0.edges[a]);
+                reg += r > 0.0f ? r : 0.0f;
+            }
+        *regret = reg;
+        return n;
     });
 }
 }

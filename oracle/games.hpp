@@ -24,6 +24,7 @@ struct KuhnGame {
     };
     static const char* name() { return "kuhn"; }
     static int rank(uint8_t card) { return card >> 1; }  // crates/kuhn/src/card.rs Card::ALL order J♠ J♥ Q♠ Q♥ K♠ K♥
+    static bool board_is(const State&, uint8_t) { return false; }  // no board in Kuhn (WorldRestrict, kuhn/src/encoder.rs:47-66)
 
     // crates/kuhn/src/game.rs:115-123 (Fisher-Yates on ALL with two range draws)
     static State root(const Philox4& p) {
@@ -119,6 +120,7 @@ struct LeducGame {
     };
     static const char* name() { return "leduc"; }
     static int rank(uint8_t card) { return card >> 1; }
+    static bool board_is(const State& s, uint8_t c) { return (s.kind == R2 || s.kind == FoldR2 || s.kind == Showdown) && s.board == c; }  // leduc/src/encoder.rs:60 board() != Some(c)
     static bool raised(uint8_t spot) { return spot == SRaised || spot == SCheckRaised; }       // game.rs:37-39
     static int actor(uint8_t spot) { return (spot == SOpen || spot == SCheckRaised) ? 0 : 1; }  // game.rs:41-46
 

@@ -100,6 +100,9 @@ struct Profile {  // strategy/book.rs (HashMap<I, HashMap<E, Encounter>> + epoch
     std::unordered_map<uint32_t, Row> rows;
     uint64_t epochs = 0;
     Hyper hyper;
+    // subgame/src/world/profile.rs:25-36: a WorldProfile is this table (`local`) over a frozen blueprint (`global`); null for a plain profile
+    const Profile* blueprint = nullptr;
+    float prior_strength = 16384.0f;  // hyperparams/warmstart.rs:27-33 (1 << 14)
 
     const Row* find(uint32_t info) const {
         auto it = rows.find(info);
@@ -118,22 +121,39 @@ struct Profile {  // strategy/book.rs (HashMap<I, HashMap<E, Encounter>> + epoch
         Row& r = entry(info);
         if (!r.present[a]) {
             r.present[a] = true;
-            r.e[a] = Encounter{0.0f /*default_policy*/, G::default_regret(r.edges[a]), 0.0f, 0};
+            // world/profile.rs:62-109: or_insert_with(|| blueprint.warmstart(&info.inner(), edge))
+            r.e[a] = blueprint ? blueprint->warmstart(info, a, r.edges[a], prior_strength)
+                               : Encounter{0.0f /*default_policy*/, G::default_regret(r.edges[a]), 0.0f, 0};
         }
         return r.e[a];
     }
-    // book.rs:93-122
+    // book.rs:93-122; world/profile.rs:118-145: an edge never written falls through to the blueprint, floored at EPSILON
     float cum_regret(uint32_t info, int a, uint8_t edge) const {
         const Row* r = find(info);
-        return (r && r->present[a]) ? r->e[a].regret : G::default_regret(edge);
+        if (r && r->present[a]) return r->e[a].regret;
+        if (blueprint) { const float g = blueprint->cum_regret(info, a, edge); return g > EPS ? g : EPS; }
+        return G::default_regret(edge);
     }
     float cum_weight(uint32_t info, int a) const {
         const Row* r = find(info);
-        return (r && r->present[a]) ? r->e[a].weight : 0.0f;
+        if (r && r->present[a]) return r->e[a].weight;
+        if (blueprint) { const float g = blueprint->cum_weight(info, a); return g > EPS ? g : EPS; }
+        return 0.0f;
     }
     uint32_t cum_visits(uint32_t info, int a) const {
         const Row* r = find(info);
-        return (r && r->present[a]) ? r->e[a].visits : 0u;
+        if (r && r->present[a]) return r->e[a].visits;
+        return blueprint ? blueprint->cum_visits(info, a) : 0u;
+    }
+    // strategy/profile.rs:94-104 warmstart (on the blueprint): weight = averaged policy * k * (k + 1) / 2, regret = cum_regret * k / max(t, 1)
+    Encounter warmstart(uint32_t info, int a, uint8_t edge, float k) const {
+        uint8_t ed[MAX_BRANCH];
+        const int n = G::choices(info, ed);
+        float w[MAXA], sum = 0.0f;  // profile.rs:40-44 averaged_distribution
+        for (int b = 0; b < n; ++b) { const float cw = cum_weight(info, b); w[b] = cw > EPS ? cw : EPS; sum = sum + w[b]; }
+        const float policy = w[a] / sum;
+        const float regret_scale = k / (float)(epochs > 1 ? epochs : 1);
+        return Encounter{policy * k * (k + 1.0f) / 2.0f, cum_regret(info, a, edge) * regret_scale, 0.0f, 0u};
     }
     int walker() const { return (int)(epochs % 2); }  // book.rs:142-144
 };
@@ -293,8 +313,10 @@ struct Solver {
         br.push_back(chosen);
     }
 
+    bool block_chance = false;  // subgame/src/world/encoder.rs:97-106: a subgame tree does not expand chance nodes (no frontier here)
     std::vector<Leaf> branches(const Tree<G>& tree, int node) const {
         uint8_t ed[MAX_BRANCH];
+        if (block_chance && G::turn(tree.game[node]) == TURN_CHANCE) return {};
         int n = G::branches(tree.game[node], ed);
         std::vector<Leaf> out;
         for (int i = 0; i < n; ++i) out.push_back(Leaf{ed[i], G::apply(tree.game[node], ed[i]), node});
@@ -442,19 +464,24 @@ struct Solver {
     // solver.rs:143-192
     void apply(const Decisions& d) {
         uint64_t epoch = profile.epochs;
+        // every update reads `profile().cum_*` (for a WorldProfile: the blueprint until the edge exists locally) and only then takes
+        // `storage().mut_*`, which is what creates the local edge (from the blueprint's warmstart)
+        uint8_t ed[MAX_BRANCH];
+        G::choices(d.info, ed);
         for (int a = 0; a < d.n; ++a) {
             if (!d.explored[a]) continue;
-            Encounter& e = profile.mut_row(d.info, a);
-            e.regret = regret_gain(regret_sched, e.regret, d.regret[a], epoch, profile.hyper);
+            const float total = profile.cum_regret(d.info, a, ed[a]);
+            profile.mut_row(d.info, a).regret = regret_gain(regret_sched, total, d.regret[a], epoch, profile.hyper);
             ++updates;
         }
         for (int a = 0; a < d.n; ++a) {
-            Encounter& e = profile.mut_row(d.info, a);
-            e.weight = weight_learn(weight_sched, e.weight, d.policy[a], epoch);
+            const float total = profile.cum_weight(d.info, a);
+            profile.mut_row(d.info, a).weight = weight_learn(weight_sched, total, d.policy[a], epoch);
         }
         for (int a = 0; a < d.n; ++a) {
+            const uint32_t n = profile.cum_visits(d.info, a);
             Encounter& e = profile.mut_row(d.info, a);
-            e.payoff += (d.payoff - e.payoff) / (float)(e.visits + 1);
+            e.payoff += (d.payoff - e.payoff) / (float)(n + 1);
         }
         for (int a = 0; a < d.n; ++a) profile.mut_row(d.info, a).visits += 1;
     }

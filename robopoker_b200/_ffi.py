@@ -141,6 +141,17 @@ def load_library():
     l.rbp_comm_barrier.argtypes = [vp]
     l.rbp_nlhe_attach_comm.argtypes = [vp, vp]
     l.rbp_solver_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
+    l.rbp_subgame_partition.argtypes = [vp, i32, i32, vp, vp]
+    l.rbp_subgame_create.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, i32, u64, P(vp)]
+    l.rbp_subgame_destroy.argtypes = [vp]
+    l.rbp_subgame_entries.argtypes = [i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp]
+    l.rbp_subgame_destroy.restype = None
+    l.rbp_subgame_step.argtypes = [vp, u64]
+    l.rbp_subgame_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
+    l.rbp_subgame_info.argtypes = [vp, P(u64), vp, vp]
+    l.rbp_subgame_export.argtypes = [vp, i32, P(ProfileRow), i32, P(i32)]
+    l.rbp_subgame_averaged.argtypes = [vp, i32, u32, P(ctypes.c_float), i32, P(i32)]
+    l.rbp_subgame_harvest.argtypes = [vp, u32, vp, vp, vp, i32, P(i32)]
     l.rbp_nlhe_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
     l.rbp_kmeans_attach_comm.argtypes = [vp, vp]
     l.rbp_solver_attach_comm.argtypes = [vp, vp]

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -94,13 +95,14 @@ struct EpochArgs {
     int regret_sched, weight_sched, fold_mode;
     float t;                // epoch as f32
     float disc_pos, disc_neg;  // DiscountedRegret x = t^1.5, t^0.5 (host libm, regret/discounted.rs:33,37)
+    int entry_plus1;        // subgame: flat node the tree starts from, + 1 (0 = the game's own root rule)
 };
 
 __device__ __forceinline__ float fmax_ref(float a, float b) { return a > b ? a : b; }
 
 // ───────────────────────────── K1: sample + value + multisplit ─────────────────────────────
 __global__ void __launch_bounds__(kTreesPerBlock)
-mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratch sc, EpochArgs ep) {
+mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, const float* __restrict__ fb_weight, Scratch sc, EpochArgs ep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int I = g.n_infos;
     float* s_sigma = reinterpret_cast<float*>(smem_raw);        // [I][4]  regret-matching policy
@@ -123,6 +125,8 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
             s_cumr[x * kMaxActions + a] = e.regret;
             r[a] = fmax_ref(e.regret, kEps);
             rd = rd + r[a];
+            // subgame/src/world/profile.rs:118-126: an edge the subgame never wrote (visits 0) reads the blueprint's weight
+            if (fb_weight != nullptr && e.visits == 0u) e.weight = fb_weight[row + a];
             w[a] = fmax_ref(e.weight, kEps);
             ws = ws + w[a];
         }
@@ -163,7 +167,9 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, Scratc
 
         // `CfrGame::root()` (kuhn/leduc game.rs root()): two-swap Fisher-Yates of the identity deck
         {
-            if (g.deck > 1) {
+            if (ep.entry_plus1 > 0) {
+                l_flat[0] = (int16_t)(ep.entry_plus1 - 1);  // subgame: `WorldRestrict::restrict`ed entry state (world/solver.rs:121-125)
+            } else if (g.deck > 1) {
                 Philox4 pr = philox4x32_10(ep.epoch, tree, 0xFFFFFFFFu, TAG_ROOT, ep.seed_lo, ep.seed_hi);
                 uint32_t i = draw_range(pr.r[0], (uint32_t)g.deck);
                 uint32_t j = 1u + draw_range(pr.r[1], (uint32_t)g.deck - 1u);
@@ -805,6 +811,32 @@ __global__ void table_reset_kernel(rbp_encounter_t* table, int n) {
     if (i < n) table[i] = rbp_encounter_t{0.0f, 0.0f, 0.0f, 0u};
 }
 
+
+// ───────────────────────────── subgame: local tables over a frozen blueprint ─────────────────────────────
+// subgame/src/world/profile.rs:62-145 + mccfr/src/strategy/profile.rs:94-104.  A WorldProfile edge that was never written reads the
+// blueprint (regret and weight floored at EPSILON); `update_regret` reads that value and then `mut_regret` creates the local edge from
+// `blueprint.warmstart` and overwrites its regret; `update_weight` then finds the edge locally with the warmstart weight.  So every
+// world's table starts at {weight: averaged policy * k * (k + 1) / 2, regret: max(blueprint regret, EPS), payoff 0, visits 0} and an
+// edge with visits = 0 reads `fb_weight` = max(blueprint weight, EPS) instead of its own weight.  One thread per infoset.
+__global__ void __launch_bounds__(128)
+subgame_seed_kernel(DevGame g, const rbp_encounter_t* __restrict__ blueprint, float k, int worlds, rbp_encounter_t* __restrict__ table, float* __restrict__ fb_weight) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.n_infos) return;
+    const int A = g.info_actions[x], row = g.info_row[x];
+    float w[kMaxActions], sum = 0.0f;  // profile.rs:40-44 averaged_distribution of the blueprint
+    for (int a = 0; a < A; ++a) { w[a] = fmax_ref(blueprint[row + a].weight, kEps); sum = sum + w[a]; }
+    for (int a = 0; a < A; ++a) {
+        const float policy = w[a] / sum;
+        rbp_encounter_t e;
+        e.weight = policy * k * (k + 1.0f) / 2.0f;
+        e.regret = fmax_ref(blueprint[row + a].regret, kEps);
+        e.payoff = 0.0f;
+        e.visits = 0u;
+        for (int wd = 0; wd < worlds; ++wd) table[(size_t)wd * g.n_rows + row + a] = e;
+        fb_weight[row + a] = w[a];
+    }
+}
+
 }  // namespace rbp
 
 // ───────────────────────────── host: handle + C ABI ─────────────────────────────
@@ -832,7 +864,11 @@ struct rbp_solver {
     uint4* flush_buf = nullptr;
     Partial* delta = nullptr;  // this rank's BATCHED partial sums
     std::vector<cudaEvent_t> events;
+    // subgame (rbp_subgame_*): `table` holds sub_worlds x n_rows rows, one table per world (WorldInfo(world, info) keys)
+    int sub_worlds = 0, sub_world = 0, sub_entry_plus1 = 0;
+    float* fb_weight = nullptr;  // [n_rows] the blueprint's weights, read for edges the subgame has not written yet
 };
+static inline rbp_encounter_t* tbl(const rbp_solver* s) { return s->table + (size_t)s->sub_world * (size_t)s->game.n_rows; }
 
 namespace {
 template <class T>
@@ -859,7 +895,8 @@ EpochArgs epoch_args(const rbp_solver* s) {
     ep.epoch = (uint32_t)s->epochs;
     ep.walker = (int)(s->epochs % 2);  // book.rs:142-144
     ep.batch = s->batch;
-    ep.tree_base = s->world_rank * s->batch;
+    ep.tree_base = s->sub_worlds ? s->sub_world : s->world_rank * s->batch;  // subgame trees draw with tree id = world
+    ep.entry_plus1 = s->sub_entry_plus1;
     ep.sampling = s->sampling;
     ep.hyper = s->hyper;
     ep.regret_sched = s->regret; ep.weight_sched = s->weight; ep.fold_mode = s->fold_mode;
@@ -869,7 +906,7 @@ EpochArgs epoch_args(const rbp_solver* s) {
     return ep;
 }
 int launch_sample(rbp_solver* s, const EpochArgs& ep) {
-    mccfr_sample_kernel<<<s->sc.nblk, kTreesPerBlock, s->sample_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
+    mccfr_sample_kernel<<<s->sc.nblk, kTreesPerBlock, s->sample_smem, s->stream>>>(s->dev, tbl(s), s->fb_weight, s->sc, ep);
     RBP_LAUNCHED();
     return RBP_OK;
 }
@@ -886,8 +923,8 @@ int launch_apply_batched(rbp_solver* s, const EpochArgs& ep, const Partial* gath
 template <int RS, int WS>
 int launch_fold_rw(rbp_solver* s, const EpochArgs& ep) {
     const bool masked = s->sampling != RBP_SAMPLING_EXTERNAL;
-    if (masked) mccfr_fold_kernel<RS, WS, true><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
-    else mccfr_fold_kernel<RS, WS, false><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, s->table, s->sc, ep);
+    if (masked) mccfr_fold_kernel<RS, WS, true><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, tbl(s), s->sc, ep);
+    else mccfr_fold_kernel<RS, WS, false><<<s->dev.n_infos, 96, s->fold_smem, s->stream>>>(s->dev, tbl(s), s->sc, ep);
     RBP_LAUNCHED();
     return RBP_OK;
 }
@@ -1210,7 +1247,7 @@ int rbp_profile_export(rbp_solver_t* s, rbp_profile_row_t* rows, int cap, int* n
     if (!s || !n_out || (cap > 0 && !rows)) return RBP_ERR_INVALID;
     RBP_CUDA(cudaSetDevice(s->device));
     std::vector<rbp_encounter_t> host(s->game.n_rows);
-    RBP_CUDA(cudaMemcpyAsync(host.data(), s->table, host.size() * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaMemcpyAsync(host.data(), tbl(s), host.size() * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
     RBP_CUDA(cudaStreamSynchronize(s->stream));
     std::vector<rbp_profile_row_t> all;
     for (size_t x = 0; x < s->game.info_key.size(); ++x)
@@ -1256,7 +1293,7 @@ int rbp_profile_averaged(rbp_solver_t* s, uint32_t info_key, float* probs, int c
     if (cap < A) return RBP_ERR_CAPACITY;
     RBP_CUDA(cudaSetDevice(s->device));
     rbp_encounter_t e[kMaxActions];
-    RBP_CUDA(cudaMemcpyAsync(e, s->table + s->game.info_row[x], A * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaMemcpyAsync(e, tbl(s) + s->game.info_row[x], A * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
     RBP_CUDA(cudaStreamSynchronize(s->stream));
     float w[kMaxActions], sum = 0.0f;  // profile.rs:41-45 (a read-out of device rows, not a compute path)
     for (int a = 0; a < A; ++a) { w[a] = e[a].weight > kEps ? e[a].weight : kEps; sum = sum + w[a]; }
@@ -1303,6 +1340,300 @@ int rbp_solver_fold_gathered(rbp_solver_t* s, const void* dev_gathered, int worl
     s->sampled = false;
     s->epochs += 1;
     RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
+
+}  // extern "C"
+
+// ───────────────────────────── safe subgame solving on the small games ─────────────────────────────
+// `WorldSolver` (crates/subgame/src/world/solver.rs:33-146) = `SubGameSolver` without an origin (crates/subgame/src/solver.rs:46-146):
+// every step samples a world from the belief, re-deals the external player's card for that world (`WorldRestrict::restrict`,
+// kuhn/src/encoder.rs:47-66, leduc/src/encoder.rs:48-70), samples ONE ExternalSampling tree from that entry state and folds it with
+// SummedRegret + LinearWeight into the world's table, which reads through to the frozen blueprint.  The epoch kernels are the
+// training ones; what is new is the entry node, the per-world table offset and the read-through of unwritten weights.
+// RNG contract: world = weighted(philox(step, 0, 0xFFFFFFFE, TAG_WORLD = 5)); the tree draws with tree id = world.
+struct rbp_subgame {
+    rbp_solver* local = nullptr;
+    int worlds = 1, external = 1;
+    float weights[8] = {};
+    int32_t world_of_rank[3] = {-1, -1, -1};
+    bool empty_belief = true;
+    int entry[8] = {};       // flat node of every world's restricted entry state
+    int cards[8][2] = {};    // its hole cards
+    uint64_t seed = 0, drawn[8] = {};
+    std::vector<rbp_encounter_t> blueprint_rows;  // host copy (Harvest and averaged read-outs fall through to it)
+};
+
+namespace {
+constexpr uint32_t TAG_WORLD = 5;
+// the flat node reached from the deal (c0, c1) by `path`; at a chance node the step names a CARD (the board survives a re-deal of a hole
+// card, its index among the remaining cards does not)
+int walk_entry(const FlatGame& G, int c0, int c1, const std::vector<int>& path_cards_or_actions, const std::vector<uint8_t>& is_card) {
+    int node = G.root_table[c0 * G.deck + c1];
+    if (node < 0) return -1;
+    for (size_t i = 0; i < path_cards_or_actions.size(); ++i) {
+        const FlatNode& nd = G.nodes[node];
+        int idx = path_cards_or_actions[i];
+        if (is_card[i]) {  // deals() order: Card::ALL ascending without the two holes
+            const int card = idx;
+            if (card == c0 || card == c1) return -1;
+            idx = card - (card > c0 ? 1 : 0) - (card > c1 ? 1 : 0);
+        }
+        if (idx < 0 || idx >= nd.n_child) return -1;
+        node = nd.first_child + idx;
+    }
+    return node;
+}
+bool reaches_chance(const FlatGame& G, int node) {
+    const FlatNode& nd = G.nodes[node];
+    if (nd.turn == TURN_CHANCE) return true;
+    for (int c = 0; c < nd.n_child; ++c) if (reaches_chance(G, nd.first_child + c)) return true;
+    return false;
+}
+}  // namespace
+
+extern "C" {
+
+// `Partition::partition::<W>` (crates/subgame/src/world/partition.rs:27-53): secrets (in ascending order) with their posterior reach ->
+// the world of every secret (world 0 = highest reach) and the probability mass of every world.  Host arithmetic on <= a few hundred floats.
+int rbp_subgame_partition(const float* reach, int n_secrets, int worlds, int32_t* world_of_secret, float* weights) {
+    if (!reach || !world_of_secret || !weights || n_secrets < 1 || worlds < 1 || worlds > 8) return RBP_ERR_INVALID;
+    float total = 0.0f;
+    for (int i = 0; i < n_secrets; ++i) total += reach[i];
+    for (int w = 0; w < worlds; ++w) weights[w] = 0.0f;
+    if (total <= 0.0f) {
+        for (int i = 0; i < n_secrets; ++i) world_of_secret[i] = 0;
+        for (int w = 0; w < worlds; ++w) weights[w] = 1.0f / (float)worlds;
+        return RBP_OK;
+    }
+    std::vector<int> order(n_secrets);
+    for (int i = 0; i < n_secrets; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return reach[a] > reach[b]; });
+    const float segment = total / (float)worlds;
+    int index = 0;
+    float bucket = 0.0f, accumulated = 0.0f;
+    for (int i : order) {
+        bucket += reach[i];
+        accumulated += reach[i];
+        world_of_secret[i] = index;
+        if (accumulated >= segment * (float)(index + 1) && index < worlds - 1) {
+            weights[index] = bucket / total;
+            index += 1;
+            bucket = 0.0f;
+        }
+    }
+    weights[index] = bucket / total;
+    return RBP_OK;
+}
+
+// Host half of `WorldSolver::new`: the restricted entry state of every world (`WorldRestrict::restrict` on the observed state) as hole
+// cards, flat node and infoset key.  No device needed.
+int rbp_subgame_entries(int game, int external, int worlds, const int32_t* world_of_rank, int c0, int c1, const uint8_t* path, int path_len,
+                        int32_t* cards16, int32_t* nodes8, uint32_t* info_keys8) {
+    if (worlds < 1 || worlds > 8 || (external != 0 && external != 1) || path_len < 0 || (path_len > 0 && !path)) return RBP_ERR_INVALID;
+    FlatGame G;
+    if (!build_flat_game(game, &G)) return RBP_ERR_INVALID;
+    if (G.deck != 6 || c0 < 0 || c0 >= 6 || c1 < 0 || c1 >= 6 || c0 == c1) { set_last_error("subgame: Kuhn / Leduc and two distinct cards"); return RBP_ERR_INVALID; }
+    // the observed state: follow the path once on the observed deal; a step at a chance node is remembered as the card it deals
+    std::vector<int> steps(path_len);
+    std::vector<uint8_t> is_card(path_len, 0);
+    int board = -1;
+    {
+        int node = G.root_table[c0 * 6 + c1];
+        for (int i = 0; i < path_len; ++i) {
+            const FlatNode& nd = G.nodes[node];
+            if (path[i] >= nd.n_child) { set_last_error("subgame: path leaves the game tree"); return RBP_ERR_INVALID; }
+            steps[i] = path[i];
+            if (nd.turn == TURN_CHANCE) {
+                int seen = -1, card = -1;
+                for (int c = 0; c < 6; ++c) { if (c == c0 || c == c1) continue; if (++seen == (int)path[i]) { card = c; break; } }
+                steps[i] = card; is_card[i] = 1; board = card;
+            }
+            node = nd.first_child + path[i];
+        }
+        if (G.nodes[node].turn > TURN_P1) { set_last_error("subgame: the entry state is not a decision node"); return RBP_ERR_INVALID; }
+    }
+    bool empty_belief = true;
+    for (int r = 0; r < 3; ++r) if (world_of_rank && world_of_rank[r] >= 0) empty_belief = false;
+    const int observed[2] = {c0, c1};
+    for (int w = 0; w < worlds; ++w) {  // WorldRestrict::restrict: the first free card whose rank the belief puts in world w
+        int hole[2] = {c0, c1};
+        for (int c = 0; c < 6; ++c) {
+            if (c == observed[1 - external] || c == board) continue;
+            if (empty_belief || world_of_rank[c >> 1] == w) { hole[external] = c; break; }
+        }
+        const int node = walk_entry(G, hole[0], hole[1], steps, is_card);
+        if (node < 0) { set_last_error("subgame: the restricted entry state is not in the game tree"); return RBP_ERR_INVALID; }
+        if (reaches_chance(G, node)) {
+            set_last_error("subgame: a chance node is reachable from the entry state; depth-limited frontiers (DepthGame with an origin) are not built");
+            return RBP_ERR_INVALID;
+        }
+        if (cards16) { cards16[2 * w] = hole[0]; cards16[2 * w + 1] = hole[1]; }
+        if (nodes8) nodes8[w] = node;
+        if (info_keys8) info_keys8[w] = G.nodes[node].info_key;
+    }
+    return RBP_OK;
+}
+
+int rbp_subgame_create(rbp_solver_t* blueprint, int external, int worlds, const int32_t* world_of_rank, const float* weights,
+                       int c0, int c1, const uint8_t* path, int path_len, uint64_t seed, rbp_subgame_t** out) {
+    if (!out) return RBP_ERR_INVALID;
+    *out = nullptr;
+    if (!blueprint || !weights) return RBP_ERR_INVALID;
+    const FlatGame& G = blueprint->game;
+    if (blueprint->sub_worlds) { set_last_error("rbp_subgame_create: the blueprint is itself a subgame"); return RBP_ERR_INVALID; }
+    int game_id = -1;
+    for (int id = 0; id < 3 && game_id < 0; ++id) { FlatGame probe; if (build_flat_game(id, &probe) && probe.nodes.size() == G.nodes.size() && probe.n_rows == G.n_rows && probe.deck == G.deck) game_id = id; }
+    if (game_id < 0) return RBP_ERR_INVALID;
+    std::unique_ptr<rbp_subgame> g(new rbp_subgame());
+    g->worlds = worlds; g->external = external; g->seed = seed;
+    {
+        int32_t cards16[16], nodes8[8];
+        const int st0 = rbp_subgame_entries(game_id, external, worlds, world_of_rank, c0, c1, path, path_len, cards16, nodes8, nullptr);
+        if (st0) return st0;
+        for (int w = 0; w < worlds; ++w) { g->weights[w] = weights[w]; g->entry[w] = nodes8[w]; g->cards[w][0] = cards16[2 * w]; g->cards[w][1] = cards16[2 * w + 1]; }
+        for (int r = 0; r < 3; ++r) { g->world_of_rank[r] = world_of_rank ? world_of_rank[r] : -1; if (g->world_of_rank[r] >= 0) g->empty_belief = false; }
+    }
+    rbp_solver_t* local = nullptr;
+    int st = rbp_solver_create(game_id, RBP_REGRET_SUMMED, RBP_WEIGHT_LINEAR, RBP_SAMPLING_EXTERNAL, RBP_FOLD_ORDERED, 1, seed, &blueprint->hyper, blueprint->device, &local);
+    if (st) return st;
+    g->local = local;
+    auto fail = [&](int code) { rbp_solver_destroy(local); return code; };
+    if (cudaSetDevice(local->device) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    rbp_encounter_t* big = nullptr;
+    if ((st = alloc(local, (size_t)worlds * G.n_rows, &big))) return fail(st);
+    if ((st = alloc(local, (size_t)G.n_rows, &local->fb_weight))) return fail(st);
+    // the blueprint's rows: a host copy for the read-outs, a device copy (on the local stream) to seed from
+    g->blueprint_rows.resize(G.n_rows);
+    if (cudaStreamSynchronize(blueprint->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    if (cudaMemcpy(g->blueprint_rows.data(), blueprint->table, (size_t)G.n_rows * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    rbp_encounter_t* bp_dev = local->table;  // the n_rows table rbp_solver_create made: scratch for the blueprint copy
+    if (cudaMemcpyAsync(bp_dev, g->blueprint_rows.data(), (size_t)G.n_rows * sizeof(rbp_encounter_t), cudaMemcpyHostToDevice, local->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    const float k = 16384.0f;  // WarmstartHyperParams::default().prior_strength = 1 << 14 (hyperparams/warmstart.rs:27-33)
+    subgame_seed_kernel<<<(local->dev.n_infos + 127) / 128, 128, 0, local->stream>>>(local->dev, bp_dev, k, worlds, big, local->fb_weight);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(local->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);
+    local->table = big;
+    local->sub_worlds = worlds;
+    local->sub_world = 0;
+    local->sub_entry_plus1 = g->entry[0] + 1;
+    *out = g.release();
+    return RBP_OK;
+}
+void rbp_subgame_destroy(rbp_subgame_t* g) {
+    if (!g) return;
+    rbp_solver_destroy(g->local);
+    delete g;
+}
+// `WorldSolver::step` n times (world/solver.rs:118-146); one stream synchronisation at the end
+int rbp_subgame_step(rbp_subgame_t* g, uint64_t n) {
+    if (!g) return RBP_ERR_INVALID;
+    rbp_solver* s = g->local;
+    RBP_CUDA(cudaSetDevice(s->device));
+    for (uint64_t i = 0; i < n; ++i) {
+        const Philox4 p = philox4x32_10((uint32_t)s->epochs, 0u, 0xFFFFFFFEu, TAG_WORLD, (uint32_t)g->seed, (uint32_t)(g->seed >> 32));
+        float total = 0.0f;  // weighted() of the RNG contract over the belief weights
+        for (int w = 0; w < g->worlds; ++w) total = total + g->weights[w];
+        const float x = draw_unit(p.r[0]) * total;
+        float cum = 0.0f;
+        int world = g->worlds - 1;
+        for (int w = 0; w < g->worlds; ++w) { cum = cum + g->weights[w]; if (x < cum) { world = w; break; } }
+        g->drawn[world] += 1;
+        s->sub_world = world;
+        s->sub_entry_plus1 = g->entry[world] + 1;
+        const EpochArgs ep = epoch_args(s);
+        int st;
+        if ((st = launch_sample(s, ep))) return st;
+        if ((st = launch_fold(s, ep))) return st;
+        s->epochs += 1;  // WorldProfile::increment
+    }
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    return RBP_OK;
+}
+// `Solver::spend` (mccfr/src/solver/solver.rs:130-137) for the real-time caller
+int rbp_subgame_spend(rbp_subgame_t* g, double seconds, uint64_t* steps_out, double* elapsed_out) {
+    if (!g || !(seconds >= 0.0)) return RBP_ERR_INVALID;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    uint64_t n = 0;
+    while (elapsed() < seconds) {
+        const int rc = rbp_subgame_step(g, 8);
+        if (rc != RBP_OK) return rc;
+        n += 8;
+    }
+    if (steps_out) *steps_out = n;
+    if (elapsed_out) *elapsed_out = elapsed();
+    return RBP_OK;
+}
+int rbp_subgame_info(rbp_subgame_t* g, uint64_t* steps, uint64_t* drawn8, int32_t* entry_cards16) {
+    if (!g) return RBP_ERR_INVALID;
+    if (steps) *steps = g->local->epochs;
+    if (drawn8) for (int w = 0; w < 8; ++w) drawn8[w] = g->drawn[w];
+    if (entry_cards16) for (int w = 0; w < 8; ++w) { entry_cards16[2 * w] = g->cards[w][0]; entry_cards16[2 * w + 1] = g->cards[w][1]; }
+    return RBP_OK;
+}
+// the rows of one world that the subgame has written (the reference's local HashMap), sorted by (info_key, action)
+int rbp_subgame_export(rbp_subgame_t* g, int world, rbp_profile_row_t* rows, int cap, int* n_out) {
+    if (!g || world < 0 || world >= g->worlds) return RBP_ERR_INVALID;
+    const int keep = g->local->sub_world;
+    g->local->sub_world = world;
+    const int st = rbp_profile_export(g->local, rows, cap, n_out);
+    g->local->sub_world = keep;
+    return st;
+}
+namespace {
+int subgame_rows(rbp_subgame_t* g, uint32_t info_key, int* A_out, rbp_encounter_t (*e)[kMaxActions]) {  // [world][action], fall-through applied
+    rbp_solver* s = g->local;
+    int x = -1;
+    for (size_t k = 0; k < s->game.info_key.size(); ++k) if (s->game.info_key[k] == info_key) { x = (int)k; break; }
+    if (x < 0) return RBP_ERR_INVALID;
+    const int A = s->game.info_actions[x], row = s->game.info_row[x];
+    RBP_CUDA(cudaSetDevice(s->device));
+    for (int w = 0; w < g->worlds; ++w)
+        RBP_CUDA(cudaMemcpyAsync(e[w], s->table + (size_t)w * s->game.n_rows + row, A * sizeof(rbp_encounter_t), cudaMemcpyDeviceToHost, s->stream));
+    RBP_CUDA(cudaStreamSynchronize(s->stream));
+    for (int w = 0; w < g->worlds; ++w)
+        for (int a = 0; a < A; ++a)
+            if (e[w][a].visits == 0u) {  // never written: world/profile.rs:118-145
+                const rbp_encounter_t& b = g->blueprint_rows[row + a];
+                e[w][a] = rbp_encounter_t{b.weight > kEps ? b.weight : kEps, b.regret > kEps ? b.regret : kEps, b.payoff, b.visits};
+            }
+    *A_out = A;
+    return RBP_OK;
+}
+}  // namespace
+// `CfrNash::averaged_policy` over `WorldInfo(world, info)` (profile.rs:40-44 on the WorldProfile)
+int rbp_subgame_averaged(rbp_subgame_t* g, int world, uint32_t info_key, float* probs, int cap, int* n_out) {
+    if (!g || !probs || !n_out || world < 0 || world >= g->worlds) return RBP_ERR_INVALID;
+    rbp_encounter_t e[8][kMaxActions];
+    int A = 0, st;
+    if ((st = subgame_rows(g, info_key, &A, e))) return st;
+    if (cap < A) return RBP_ERR_CAPACITY;
+    float w[kMaxActions], sum = 0.0f;
+    for (int a = 0; a < A; ++a) { w[a] = e[world][a].weight > kEps ? e[world][a].weight : kEps; sum = sum + w[a]; }
+    for (int a = 0; a < A; ++a) probs[a] = w[a] / sum;
+    *n_out = A;
+    return RBP_OK;
+}
+// `Harvest::harvest` (world/solver.rs:148-191) at a base infoset: refined[a] = sum over worlds of the iterated (regret-matching) policy / W,
+// visits[a] = sum of cum_visits, regret = sum over edges and worlds of max(cum_regret, 0)
+int rbp_subgame_harvest(rbp_subgame_t* g, uint32_t info_key, float* refined, uint32_t* visits, float* regret, int cap, int* n_out) {
+    if (!g || !refined || !visits || !regret || !n_out) return RBP_ERR_INVALID;
+    rbp_encounter_t e[8][kMaxActions];
+    int A = 0, st;
+    if ((st = subgame_rows(g, info_key, &A, e))) return st;
+    if (cap < A) return RBP_ERR_CAPACITY;
+    for (int a = 0; a < A; ++a) { refined[a] = 0.0f; visits[a] = 0u; }
+    for (int w = 0; w < g->worlds; ++w) {
+        float r[kMaxActions], rd = 0.0f;
+        for (int a = 0; a < A; ++a) { r[a] = e[w][a].regret > kEps ? e[w][a].regret : kEps; rd = rd + r[a]; }
+        for (int a = 0; a < A; ++a) refined[a] += r[a] / rd / (float)g->worlds;
+    }
+    float reg = 0.0f;
+    for (int a = 0; a < A; ++a)
+        for (int w = 0; w < g->worlds; ++w) { visits[a] += e[w][a].visits; reg += e[w][a].regret > 0.0f ? e[w][a].regret : 0.0f; }
+    *regret = reg;
+    *n_out = A;
     return RBP_OK;
 }
 

@@ -1,0 +1,89 @@
+"""GPU parity for the safe subgame solver (`rbp_subgame_*`, csrc/mccfr.cu) against oracle/subgame.hpp: bit-exact local tables per world.
+
+HARDWARE STATUS: this path was written after the round's GPU minutes were spent — the oracle, the host half (`rbp_subgame_entries`,
+`rbp_subgame_partition`) and the arithmetic of the table seeding are checked on the CPU (tests/test_oracle_subgame.py), the device half has
+not run on a B200 yet.  The module is therefore marked xfail(strict=False): it cannot turn the suite red, and an XPASS line in the summary means
+the device path matches the oracle bit for bit.  It sorts last among the test files, after every validated path.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="subgame device path not yet run on hardware (GPU budget exhausted before it was written); XPASS = bit-exact")]
+
+CASES = [
+    # game, blueprint epochs, external, observed deal, path, worlds, steps
+    ("kuhn", 4096, 1, (2, 5), (), 2, 3000),            # kuhn/src/solver.rs `subgame!`: from the dealt root, P1 external
+    ("kuhn", 4096, 0, (0, 3), (0,), 3, 3000),          # `subgame_after_check`
+    ("kuhn", 4096, 0, (4, 1), (1,), 2, 3000),          # `subgame_after_bet`
+    ("kuhn", 64, 1, (1, 0), (), 1, 500),               # one world, barely trained blueprint (most rows fall through)
+    ("leduc", 8192, 1, (1, 4), (0, 0, 1), 2, 3000),    # second betting round after check-check and the board
+    ("leduc", 8192, 0, (5, 2), (1, 1, 0, 0), 2, 3000),
+]
+
+
+def belief_for(oracle, cards, external, worlds):
+    reach = [0.0, 0.0, 0.0]
+    for c in range(6):
+        if c != cards[1 - external]:
+            reach[c >> 1] += 1.0 + 0.25 * (c >> 1)
+    return oracle.partition(reach, worlds)
+
+
+def make(rbp, oracle, game, epochs, external, cards, path, worlds, seed=11):
+    g_bp = rbp.Solver(game, "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(epochs)
+    o_bp = oracle.OracleSolver(game, "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(epochs)
+    assert g_bp.profile_rows().tobytes() == o_bp.profile_rows().tobytes()             # same blueprint to start from
+    world_of, weights = belief_for(oracle, cards, external, worlds)
+    g = rbp.subgame.WorldSolver(g_bp, external, (world_of, weights), cards, path, seed=seed)
+    o = oracle.OracleSubgame(o_bp, external, world_of, weights, cards, path, seed=seed)
+    return g, o, g_bp
+
+
+@pytest.mark.parametrize("game,epochs,external,cards,path,worlds,steps", CASES)
+def test_bit_exact_against_oracle(rbp, oracle, game, epochs, external, cards, path, worlds, steps):
+    g, o, g_bp = make(rbp, oracle, game, epochs, external, cards, path, worlds)
+    for chunk in (1, 1, 30, steps - 32):                                              # the first writes, then the bulk
+        g.step(chunk); o.step(chunk)
+        info = g.info()
+        assert info["t"] == o.t and np.array_equal(info["drawn"], o.drawn())
+        for w in range(worlds):
+            assert info["entries"][w] == o.entry(w)
+            a, b = g.profile_rows(w), o.profile_rows(w)
+            assert len(a) == len(b) and a.tobytes() == b.tobytes(), (chunk, w)
+    keys = sorted({int(k) for w in range(worlds) for k in o.profile_rows(w)["info_key"]})
+    for key in keys:
+        for w in range(worlds):
+            assert np.array_equal(g.averaged_distribution(w, key).view(np.uint32), o.averaged_distribution(w, key).view(np.uint32))
+        gr, gv, gx = g.harvest(key)
+        orr, ov, ox = o.harvest(key)
+        assert np.array_equal(gr.view(np.uint32), orr.view(np.uint32)) and np.array_equal(gv, ov) and np.float32(gx) == np.float32(ox)
+    g.close()
+    g_bp.step(3)                                                                      # the blueprint handle is untouched and still trains
+
+
+def test_kuhn_subgame_nash_on_device(rbp, oracle):
+    # kuhn/src/solver.rs `subgame_nash`: K|B and K|XB call > 0.90 averaged over the worlds (2^18-epoch blueprint, 2^16 subgame steps)
+    from robopoker_b200 import kuhn_info
+
+    bp = rbp.Solver("kuhn", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=0).step(1 << 18)
+    cards, external = (2, 5), 1
+    reach = [0.0, 0.0, 0.0]
+    for c in range(6):
+        if c != cards[1 - external]:
+            reach[c >> 1] += 1.0
+    sg = rbp.subgame.WorldSolver(bp, external, rbp.subgame.partition(reach, 2), cards, (), seed=1).solve(1 << 16)
+    pol = lambda rank, hist: float(np.mean([sg.averaged_distribution(w, kuhn_info(rank, hist))[1] for w in range(2)]))
+    assert pol("K", "Bet") > 0.90 and pol("K", "CheckBet") > 0.90
+
+
+def test_spend_and_refusals(rbp, oracle):
+    bp = rbp.Solver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(256)
+    with pytest.raises(rbp.RbpError):                                                 # first round: the board deal is reachable
+        rbp.subgame.WorldSolver(bp, 1, (None, [1.0]), (0, 3), ())
+    sg = rbp.subgame.WorldSolver(bp, 1, (None, [0.5, 0.5]), (0, 3), (1, 1, 2))
+    n, dt = sg.spend(0.05)
+    assert n >= 8 and dt >= 0.05 and sg.info()["t"] == n
+    assert sum(len(sg.profile_rows(w)) for w in range(2)) > 0
