@@ -108,6 +108,52 @@ private:
     int batch_;
 };
 
+// `WorldSolver` (crates/subgame/src/world/solver.rs:33-146) = `SubGameSolver::new` (crates/subgame/src/solver.rs:46-70) on Kuhn / Leduc
+struct Belief {                                                                                                          // world/belief.rs:20-27
+    std::vector<int32_t> world_of_rank;  // empty = no members: every secret is remembered
+    std::vector<float> weights;
+};
+inline Belief partition(const std::vector<float>& reach, int worlds) {                                                   // world/partition.rs:27-53
+    Belief b{std::vector<int32_t>(reach.size()), std::vector<float>((size_t)worlds)};
+    ok(rbp_subgame_partition(reach.data(), (int)reach.size(), worlds, b.world_of_rank.data(), b.weights.data()), "rbp_subgame_partition");
+    return b;
+}
+class WorldSolver {
+public:
+    struct Harvested { std::vector<float> refined; std::vector<uint32_t> visits; float regret; };                        // mccfr Harvested<E>
+    WorldSolver(const Solver& blueprint, int external, const Belief& belief, int c0, int c1, const std::vector<uint8_t>& path = {}, uint64_t seed = 0)
+        : worlds_((int)belief.weights.size()) {
+        rbp_subgame_t* h = nullptr;
+        ok(rbp_subgame_create(blueprint.raw(), external, worlds_, belief.world_of_rank.empty() ? nullptr : belief.world_of_rank.data(), belief.weights.data(), c0, c1,
+                              path.empty() ? nullptr : path.data(), (int)path.size(), seed, &h), "rbp_subgame_create");
+        h_ = decltype(h_)(h);
+    }
+    WorldSolver& step(uint64_t n = 1) { ok(rbp_subgame_step(h_.get(), n), "rbp_subgame_step"); return *this; }           // world/solver.rs:118-146
+    WorldSolver& solve(uint64_t trees) { return step(trees); }                                                          // batch_size() = 1
+    std::pair<uint64_t, double> spend(double seconds) {                                                                 // Solver::spend
+        uint64_t n = 0; double dt = 0;
+        ok(rbp_subgame_spend(h_.get(), seconds, &n, &dt), "rbp_subgame_spend");
+        return {n, dt};
+    }
+    std::vector<rbp_profile_row_t> into_profile(int world) const {                                                       // WorldProfile::local of one world
+        std::vector<rbp_profile_row_t> rows(4096);
+        int n = 0;
+        ok(rbp_subgame_export(h_.get(), world, rows.data(), (int)rows.size(), &n), "rbp_subgame_export");
+        rows.resize((size_t)n);
+        return rows;
+    }
+    Harvested harvest(uint32_t info_key) const {                                                                         // world/solver.rs:148-191
+        float refined[8], regret = 0; uint32_t visits[8]; int n = 0;
+        ok(rbp_subgame_harvest(h_.get(), info_key, refined, visits, &regret, 8, &n), "rbp_subgame_harvest");
+        return Harvested{std::vector<float>(refined, refined + n), std::vector<uint32_t>(visits, visits + n), regret};
+    }
+    int worlds() const { return worlds_; }
+
+private:
+    detail::Handle<rbp_subgame_t, rbp_subgame_destroy> h_;
+    int worlds_;
+};
+
 class IsoSet;
 
 // `Nlhe<R, W, S>`; the defaults are `Flagship` (crates/nlhe/src/lib.rs:86-90).
