@@ -146,6 +146,11 @@ typedef struct rbp_subgame rbp_subgame_t;
 /* `Partition::partition::<W>` (world/partition.rs:27-53): posterior reach of every secret (ascending secret order) -> its world
  * (0 = highest reach) and the probability mass of every world */
 int rbp_subgame_partition(const float* reach, int n_secrets, int worlds, int32_t* world_of_secret, float* weights);
+/* the action-conditioned posterior over the external player's rank (kuhn/src/solver.rs `subgame_with_reach_conditioned_posterior`): per card
+ * the external player could hold, `Solver::external_reach` (mccfr/src/solver/solver.rs:198-211) along the path under the blueprint's averaged
+ * policy, summed per rank (`Posterior::add`).  `rows` = rbp_profile_export of the blueprint.  Host arithmetic, no device needed. */
+int rbp_subgame_posterior(int game, const rbp_profile_row_t* rows, int n_rows, int external, int c0, int c1, const uint8_t* path, int path_len,
+                          float* reach3);
 /* `WorldSolver::new(encoder, profile, external, belief, recall)`: `blueprint` = a trained Kuhn / Leduc solver (its table is copied: the
  * blueprint may be destroyed afterwards); belief = world of every rank (NULL = `Belief` without members: every secret is remembered)
  * + `worlds` weights; recall = the observed deal (c0, c1: card = 2 * rank + suit, `Card::ALL` order) and the path of branch indices

@@ -135,6 +135,7 @@ def _sub():
     if not getattr(l, "_sub_ready", False):
         vp, u64, i32, u32, f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_float
         l.orc_partition.argtypes = [vp, i32, i32, vp, vp]
+        l.orc_subgame_posterior.argtypes = [vp, i32, i32, i32, vp, i32, vp]
         l.orc_subgame_create.restype = vp
         l.orc_subgame_create.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, i32, u64]
         l.orc_subgame_destroy.argtypes = [vp]
@@ -160,6 +161,14 @@ def partition(reach, worlds):
     world_of, weights = np.zeros(len(reach), np.int32), np.zeros(worlds, np.float32)
     _sub().orc_partition(reach.ctypes.data, len(reach), worlds, world_of.ctypes.data, weights.ctypes.data)
     return world_of, weights
+
+
+def subgame_posterior(blueprint, external, cards, path=()):
+    """Reach per rank of the external player's hand given the path (external_reach per card, Posterior::add per rank)."""
+    p = np.ascontiguousarray(list(path), dtype=np.uint8)
+    out = np.zeros(3, np.float32)
+    _sub().orc_subgame_posterior(blueprint._h, external, cards[0], cards[1], p.ctypes.data if len(p) else None, len(p), out.ctypes.data)
+    return out
 
 
 class OracleSubgame:

@@ -147,6 +147,49 @@ template <class F>
 static auto with_sub(OrcSubgame* g, F f) { return g->game == 0 ? f(*g->kuhn) : f(*g->leduc); }
 
 extern "C" {
+// kuhn/src/solver.rs `subgame_with_reach_conditioned_posterior` + mccfr/src/solver/solver.rs:198-211 external_reach: per card the external
+// player could hold, the product along the path of the blueprint's averaged policy at the external player's decisions; summed per rank
+void orc_subgame_posterior(OrcSolver* bp, int external, int c0, int c1, const uint8_t* path, int path_len, float* reach3) {
+    for (int r = 0; r < 3; ++r) reach3[r] = 0.0f;
+    if (bp->game == 0) {
+        using G = KuhnGame;
+        G::State obs = entry_state<G>(G::State{{(uint8_t)c0, (uint8_t)c1}, G::Open}, path, path_len);
+        for (uint8_t c = 0; c < 6; ++c) {
+            if (c == obs.hole[1 - external] || G::board_is(obs, c)) continue;
+            G::State s{{(uint8_t)c0, (uint8_t)c1}, G::Open};
+            s.hole[external] = c;
+            float reach = 1.0f;
+            G::State o = G::State{{(uint8_t)c0, (uint8_t)c1}, G::Open};  // the observed trajectory names the edges
+            for (int i = 0; i < path_len; ++i) {
+                uint8_t ed[MAX_BRANCH];
+                G::branches(o, ed);
+                const uint8_t edge = ed[path[i]];
+                if ((int)G::turn(s) == external) reach = reach * bp->kuhn.averaged_policy(G::info_key(s), edge);
+                s = G::apply(s, edge); o = G::apply(o, edge);
+            }
+            reach3[G::rank(c)] += reach;
+        }
+    } else {
+        using G = LeducGame;
+        const G::State root{{(uint8_t)c0, (uint8_t)c1}, G::R1, 0, G::SOpen, 0, 0};
+        G::State obs = entry_state<G>(root, path, path_len);
+        for (uint8_t c = 0; c < 6; ++c) {
+            if (c == obs.hole[1 - external] || G::board_is(obs, c)) continue;
+            G::State s = root;
+            s.hole[external] = c;
+            float reach = 1.0f;
+            G::State o = root;
+            for (int i = 0; i < path_len; ++i) {
+                uint8_t ed[MAX_BRANCH];
+                G::branches(o, ed);
+                const uint8_t edge = ed[path[i]];
+                if ((int)G::turn(s) == external) reach = reach * bp->leduc.averaged_policy(G::info_key(s), edge);
+                s = G::apply(s, edge); o = G::apply(o, edge);
+            }
+            reach3[G::rank(c)] += reach;
+        }
+    }
+}
 void orc_partition(const float* reach, int n, int worlds, int32_t* world_of, float* weights) { partition(reach, n, worlds, world_of, weights); }
 OrcSubgame* orc_subgame_create(OrcSolver* bp, int external, int worlds, const int32_t* world_of_rank, const float* weights, int c0, int c1,
                                const uint8_t* path, int path_len, uint64_t seed) {

@@ -142,6 +142,7 @@ def load_library():
     l.rbp_nlhe_attach_comm.argtypes = [vp, vp]
     l.rbp_solver_spend.argtypes = [vp, ctypes.c_double, P(u64), P(ctypes.c_double)]
     l.rbp_subgame_partition.argtypes = [vp, i32, i32, vp, vp]
+    l.rbp_subgame_posterior.argtypes = [i32, P(ProfileRow), i32, i32, i32, i32, vp, i32, vp]
     l.rbp_subgame_create.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, i32, u64, P(vp)]
     l.rbp_subgame_destroy.argtypes = [vp]
     l.rbp_subgame_entries.argtypes = [i32, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp]

@@ -1475,6 +1475,66 @@ int rbp_subgame_entries(int game, int external, int worlds, const int32_t* world
     return RBP_OK;
 }
 
+// The action-conditioned posterior over the external player's rank at the observed state (kuhn/src/solver.rs
+// `subgame_with_reach_conditioned_posterior`): for every card the external player could hold, `Solver::external_reach`
+// (mccfr/src/solver/solver.rs:198-211) = the product, along the recall's path, of the blueprint's averaged policy at the external
+// player's own decisions; summed per rank (`Posterior::add`).  Host arithmetic over the blueprint's exported rows; no device needed.
+int rbp_subgame_posterior(int game, const rbp_profile_row_t* rows, int n_rows, int external, int c0, int c1, const uint8_t* path, int path_len,
+                          float* reach3) {
+    if (!reach3 || (n_rows > 0 && !rows) || n_rows < 0 || (external != 0 && external != 1) || path_len < 0 || (path_len > 0 && !path)) return RBP_ERR_INVALID;
+    FlatGame G;
+    if (!build_flat_game(game, &G)) return RBP_ERR_INVALID;
+    if (G.deck != 6 || c0 < 0 || c0 >= 6 || c1 < 0 || c1 >= 6 || c0 == c1) { set_last_error("subgame: Kuhn / Leduc and two distinct cards"); return RBP_ERR_INVALID; }
+    std::vector<float> weight(G.n_rows, 0.0f);  // RefProf::cum_weight, 0 where the blueprint holds no row
+    for (int i = 0; i < n_rows; ++i) {
+        int x = -1;
+        for (size_t k = 0; k < G.info_key.size(); ++k) if (G.info_key[k] == rows[i].info_key) { x = (int)k; break; }
+        if (x < 0 || rows[i].action >= G.info_actions[x]) { set_last_error("subgame: unknown (info_key, action) in the blueprint rows"); return RBP_ERR_INVALID; }
+        weight[G.info_row[x] + (int)rows[i].action] = rows[i].row.weight;
+    }
+    std::vector<int> steps(path_len);
+    std::vector<uint8_t> is_card(path_len, 0);
+    int board = -1;
+    {
+        int node = G.root_table[c0 * 6 + c1];
+        for (int i = 0; i < path_len; ++i) {
+            const FlatNode& nd = G.nodes[node];
+            if (path[i] >= nd.n_child) { set_last_error("subgame: path leaves the game tree"); return RBP_ERR_INVALID; }
+            steps[i] = path[i];
+            if (nd.turn == TURN_CHANCE) {
+                int seen = -1, card = -1;
+                for (int c = 0; c < 6; ++c) { if (c == c0 || c == c1) continue; if (++seen == (int)path[i]) { card = c; break; } }
+                steps[i] = card; is_card[i] = 1; board = card;
+            }
+            node = nd.first_child + path[i];
+        }
+    }
+    const int observed[2] = {c0, c1};
+    for (int r = 0; r < 3; ++r) reach3[r] = 0.0f;
+    for (int c = 0; c < 6; ++c) {
+        if (c == observed[1 - external] || c == board) continue;
+        int hole[2] = {c0, c1};
+        hole[external] = c;
+        int node = G.root_table[hole[0] * 6 + hole[1]];
+        float reach = 1.0f;  // Iterator::product over f32
+        for (int i = 0; i < path_len && node >= 0; ++i) {
+            const FlatNode& nd = G.nodes[node];
+            int idx = steps[i];
+            if (is_card[i]) idx = idx - (idx > hole[0] ? 1 : 0) - (idx > hole[1] ? 1 : 0);
+            if (nd.turn == external) {  // averaged_policy(info, edge) = max(w, EPS) / sum (profile.rs:40-44)
+                const int A = G.info_actions[nd.info], row = G.info_row[nd.info];
+                float sum = 0.0f;
+                for (int a = 0; a < A; ++a) sum = sum + (weight[row + a] > kEps ? weight[row + a] : kEps);
+                const float w = weight[row + idx] > kEps ? weight[row + idx] : kEps;
+                reach = reach * (w / sum);
+            }
+            node = nd.first_child + idx;
+        }
+        reach3[c >> 1] += reach;
+    }
+    return RBP_OK;
+}
+
 int rbp_subgame_create(rbp_solver_t* blueprint, int external, int worlds, const int32_t* world_of_rank, const float* weights,
                        int c0, int c1, const uint8_t* path, int path_len, uint64_t seed, rbp_subgame_t** out) {
     if (!out) return RBP_ERR_INVALID;

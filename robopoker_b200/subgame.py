@@ -25,6 +25,19 @@ def partition(reach, worlds):
     return world_of, weights
 
 
+def posterior(game, blueprint_rows, external, cards, path=()):
+    """Reach of every rank the external player could hold, conditioned on the path (`Solver::external_reach` per card, `Posterior::add` per
+    rank); `blueprint_rows` = `Solver.profile_rows()` of the blueprint.  Host arithmetic."""
+    from .solver import GAMES
+    rows = np.ascontiguousarray(blueprint_rows, dtype=ROW_DTYPE)
+    p = np.ascontiguousarray(list(path), dtype=np.uint8)
+    out = np.zeros(3, np.float32)
+    ptr = rows.ctypes.data_as(ctypes.POINTER(_ffi.ProfileRow))
+    _ffi.check(_ffi.lib().rbp_subgame_posterior(GAMES[game], ptr, len(rows), int(external), int(cards[0]), int(cards[1]),
+                                                p.ctypes.data if len(p) else None, len(p), out.ctypes.data), "rbp_subgame_posterior")
+    return out
+
+
 def entries(game, external, world_of_rank, worlds, cards, path=()):
     """Host half of `WorldSolver::new` (no device): per world the restricted deal, the flat node and the infoset key of the entry state."""
     from .solver import GAMES

@@ -105,6 +105,40 @@ def test_kuhn_subgame_nash(oracle, kuhn_blueprint, external, cards, path):
     assert sg.sum_regret() < 0.05
 
 
+def test_reach_conditioned_posterior(oracle, rbp, kuhn_blueprint):
+    # kuhn/src/solver.rs `subgame_with_reach_conditioned_posterior`: after P0 checks and P1 bets the posterior over P1's hand is weighted by
+    # the blueprint's probability of that bet (K bets ~always after a check, J / Q less), the subgame converges and K|XB still calls
+    cards, path, external = (2, 5), (0, 1), 1                                        # P0 holds Q; Check, Bet
+    prior = oracle.subgame_posterior(kuhn_blueprint, external, cards, path)
+    lib_prior = rbp.subgame.posterior("kuhn", kuhn_blueprint.profile_rows(), external, cards, path)   # the library's host arithmetic
+    assert np.array_equal(prior.view(np.uint32), lib_prior.view(np.uint32))
+    assert prior[2] > prior[0] and prior[2] > prior[1] and prior[2] > 1.8            # two K cards, each bet with probability ~1
+    world_of, weights = oracle.partition(prior, 2)
+    assert world_of[2] == 0                                                           # K carries the most reach: world 0
+    sg = oracle.OracleSubgame(kuhn_blueprint, external, world_of, weights, cards, path, seed=5).step(N16)
+    assert sg.sum_regret() < 0.01
+    assert subpolicy(sg, 2, "K", "CheckBet", 1) > 0.90
+
+
+def test_posterior_library_equals_oracle(oracle, rbp):
+    n = 0
+    for game, epochs in (("kuhn", 3000), ("leduc", 20000)):
+        bp = oracle.OracleSolver(game, "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=2).step(epochs)
+        rows = bp.profile_rows()
+        paths = [(), (0,), (1,), (0, 1)] if game == "kuhn" else [(0,), (1, 1), (0, 0, 2), (0, 0, 1, 0), (1, 1, 3, 1), (0, 1, 1, 0, 0)]
+        for c0, c1 in itertools.permutations(range(6), 2):
+            for path in paths:
+                for external in (0, 1):
+                    try:
+                        got = rbp.subgame.posterior(game, rows, external, (c0, c1), path)
+                    except rbp.RbpError:
+                        continue
+                    want = oracle.subgame_posterior(bp, external, (c0, c1), path)
+                    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (game, c0, c1, path, external, got, want)
+                    n += 1
+    assert n > 500
+
+
 def test_first_write_reads_through_to_the_blueprint(oracle, kuhn_blueprint):
     # world/profile.rs + strategy/profile.rs:94-104: the first update of an edge starts from max(blueprint regret, EPS) and from the
     # warmstart weight = averaged policy * k * (k + 1) / 2 (k = 2^14); at t = 0 LinearWeight adds policy * 0
