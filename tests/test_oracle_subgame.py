@@ -158,6 +158,35 @@ def test_first_write_reads_through_to_the_blueprint(oracle, kuhn_blueprint):
     assert kuhn_info("Q", "Open") in {int(r["info_key"]) for r in rows}               # t = 0: the walker is seat 0, holding Q
 
 
+@pytest.mark.parametrize("external,cards,path,entry_node,epochs", [(1, (2, 5), (), 0, 4096), (0, (0, 3), (0,), 1, 4096), (0, (4, 1), (1,), 2, 64), (1, (1, 0), (0, 1), 3, 300)])
+def test_dense_table_model_equals_the_world_profile(oracle, external, cards, path, entry_node, epochs):
+    # tests/subgame_dense_model.py restates the step the way the device does it (seeded dense tables per world, `visits == 0` -> blueprint
+    # weight, LIFO tree from the entry node, ordered fold); the oracle keeps the reference's two-level HashMap profile.  Bit-identical rows.
+    from subgame_dense_model import DenseSubgame
+
+    bp = oracle.OracleSolver("kuhn", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(epochs)
+    reach = [0.0, 0.0, 0.0]
+    for c in range(6):
+        if c != cards[1 - external]:
+            reach[c >> 1] += 1.0 + 0.25 * (c >> 1)
+    world_of, weights = oracle.partition(reach, 2)
+    o = oracle.OracleSubgame(bp, external, world_of, weights, cards, path, seed=11)
+    d = DenseSubgame(oracle.philox, bp.profile_rows(), 2, weights, [o.entry(w) for w in range(2)], entry_node, seed=11)
+    for n in (1, 1, 2, 60, 400):
+        o.step(n)
+        for _ in range(n):
+            d.step()
+        assert d.drawn == [int(x) for x in o.drawn()]
+        for w in range(2):
+            want = o.profile_rows(w)
+            got = d.rows(w)
+            assert len(got) == len(want), (n, w)
+            for g, r in zip(got, want):
+                assert g[0] == int(r["info_key"]) and g[1] == int(r["action"]) and g[5] == int(r["visits"])
+                for x, name in ((g[2], "weight"), (g[3], "regret"), (g[4], "payoff")):
+                    assert np.float32(x).view(np.uint32) == np.float32(r[name]).view(np.uint32), (n, w, g, r)
+
+
 def digest(rows):
     return hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest()
 
