@@ -105,7 +105,9 @@ def main_turn(args, ranks, Clocks, peaks, oracle_native):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "elkan_step_kernel", "achieved": alg / kernel_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / kernel_s / 1e9 / peak, "peak_source": peak_src, "traffic": None,
-                             "kernel_ms": {"step (events on the library stream)": dev_ms}, "note": "whole step against the bounds-stream model 112 + 8k + 9 bytes per point"},
+                             "kernel_ms": {"step (events on the library stream)": dev_ms}, "note": "whole step against the bounds-stream model 112 + 8k + 9 bytes per point; ncu of the shipped step at 3 M x 500 (profiles/r2ai_elkan_v8_ncu.txt): "
+                                     "DRAM 12.45 GB per launch = 8.3 B per (point, centroid) pair, i.e. the model's traffic and nothing re-read; the early, loosely "
+                                     "pruned iterations are bound by the distance arithmetic, not by this stream (DESIGN 3)"},
                 "reassigned_last": int(last.reassignment), "distance_evals_upper_bound_per_s": n_total * k / (ms * 1e-3)}
         if world == 1 and not args.skip_cpu_baseline:
             oracle = oracle_native()
