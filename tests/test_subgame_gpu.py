@@ -2,7 +2,7 @@
 
 HARDWARE STATUS: this path was written after the round's GPU minutes were spent — the oracle, the host half (`rbp_subgame_entries`,
 `rbp_subgame_partition`) and the arithmetic of the table seeding are checked on the CPU (tests/test_oracle_subgame.py), the device half has
-not run on a B200 yet.  The module is therefore marked xfail(strict=False): it cannot turn the suite red, and an XPASS line in the summary means
+not run on a B200 yet (its kernel source has, on the CPU, under the SIMT shim of tests/test_simt_mccfr.py).  The module is therefore marked xfail(strict=False): it cannot turn the suite red, and an XPASS line in the summary means
 the device path matches the oracle bit for bit.  It sorts last among the test files, after every validated path.
 """
 import itertools
