@@ -155,7 +155,8 @@ int rbp_subgame_posterior(int game, const rbp_profile_row_t* rows, int n_rows, i
  * blueprint may be destroyed afterwards); belief = world of every rank (NULL = `Belief` without members: every secret is remembered)
  * + `worlds` weights; recall = the observed deal (c0, c1: card = 2 * rank + suit, `Card::ALL` order) and the path of branch indices
  * (`branches()` order; at a chance node: index among the cards still in the deck) from the dealt root to the entry state.
- * RBP_ERR_INVALID if a chance node is reachable from the entry state (that needs the frontier machinery). */
+ * The tree of a step stops at chance nodes (world/encoder.rs:97-106); such a leaf is worth `frontier_payoff` of its nearest decision
+ * ancestor (mccfr/src/strategy/nash.rs:50-79: the stored V(I), local or the blueprint's). */
 int rbp_subgame_create(rbp_solver_t* blueprint, int external, int worlds, const int32_t* world_of_rank /* [3] or NULL */, const float* weights,
                        int c0, int c1, const uint8_t* path, int path_len, uint64_t seed, rbp_subgame_t** out);
 void rbp_subgame_destroy(rbp_subgame_t* g);

@@ -145,6 +145,11 @@ struct Profile {  // strategy/book.rs (HashMap<I, HashMap<E, Encounter>> + epoch
         if (r && r->present[a]) return r->e[a].visits;
         return blueprint ? blueprint->cum_visits(info, a) : 0u;
     }
+    float cum_payoff(uint32_t info, int a) const {  // book.rs:93-122; world/profile.rs:133-138 (no floor)
+        const Row* r = find(info);
+        if (r && r->present[a]) return r->e[a].payoff;
+        return blueprint ? blueprint->cum_payoff(info, a) : 0.0f;
+    }
     // strategy/profile.rs:94-104 warmstart (on the blueprint): weight = averaged policy * k * (k + 1) / 2, regret = cum_regret * k / max(t, 1)
     Encounter warmstart(uint32_t info, int a, uint8_t edge, float k) const {
         uint8_t ed[MAX_BRANCH];
@@ -359,9 +364,20 @@ struct Solver {
         }
         return cf / sm;
     }
+    // nash.rs:50-79 terminal_value of a childless node: the game's payoff at a terminal; at a chance node that was not expanded (a
+    // subgame tree stops at chance nodes, subgame/src/world/encoder.rs:97-106) `frontier_payoff` = cum_payoff(info, first choice) of the
+    // nearest non-chance ancestor's infoset — V(I) as stored, taken for `hero` without a change of sign, as the reference does
+    float terminal_value(const Tree<G>& tree, int node, int hero) const {
+        const Turn t = G::turn(tree.game[node]);
+        if (t == TURN_TERMINAL) return G::payoff(tree.game[node], hero);
+        int a = node;
+        if (t == TURN_CHANCE) { do { a = tree.parent[a]; } while (a >= 0 && G::turn(tree.game[a]) == TURN_CHANCE); }
+        if (a < 0) return 0.0f;  // "chance node cannot be root of game"
+        return profile.cum_payoff(tree.info[a], 0);
+    }
     // flow.rs:182-216 recursed_value
     float recursed_value(const Tree<G>& tree, int hero, int node, float rel, float smp) const {
-        if (tree.head[node] < 0) return rel / smp * G::payoff(tree.game[node], hero);  // nash.rs:66-79 terminal
+        if (tree.head[node] < 0) return rel / smp * terminal_value(tree, node, hero);
         Turn t = G::turn(tree.game[node]);
         bool chance = t == TURN_CHANCE, walk = (int)t == profile.walker();
         InfoView v{};

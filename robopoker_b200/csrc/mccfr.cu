@@ -112,6 +112,7 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, const 
     uint32_t* s_woff = s_bits + 4 * I;                          // [4][I] warp offsets
     uint32_t* s_cnt = s_woff + 4 * I;                           // [I]
     uint32_t* s_off = s_cnt + I;                                // [I]
+    float* s_pay = reinterpret_cast<float*>(s_off + I);         // [I]  V(I) = cum_payoff(info, first choice) (subgame chance leaves)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -125,8 +126,9 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, const 
             s_cumr[x * kMaxActions + a] = e.regret;
             r[a] = fmax_ref(e.regret, kEps);
             rd = rd + r[a];
-            // subgame/src/world/profile.rs:118-126: an edge the subgame never wrote (visits 0) reads the blueprint's weight
-            if (fb_weight != nullptr && e.visits == 0u) e.weight = fb_weight[row + a];
+            // subgame/src/world/profile.rs:118-138: an edge the subgame never wrote (visits 0) reads the blueprint's weight and payoff
+            if (fb_weight != nullptr && e.visits == 0u) { e.weight = fb_weight[row + a]; e.payoff = fb_weight[g.n_rows + row + a]; }
+            if (a == 0) s_pay[x] = e.payoff;  // nash.rs:50-56 frontier_payoff: the first choice's stored V(I)
             w[a] = fmax_ref(e.weight, kEps);
             ws = ws + w[a];
         }
@@ -186,6 +188,7 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, const 
             const FlatNode nd = g.nodes[l_flat[k]];
             const int n = nd.n_child;
             if (n == 0) return;
+            if (ep.entry_plus1 > 0 && nd.turn == TURN_CHANCE) return;  // subgame/src/world/encoder.rs:97-106: a subgame tree stops at chance nodes
             if (nd.turn == ep.walker) {
                 uint32_t keep = (1u << n) - 1u;
                 bool prune = ep.sampling == RBP_SAMPLING_PRUNABLE;
@@ -267,7 +270,12 @@ mccfr_sample_kernel(DevGame g, const rbp_encounter_t* __restrict__ table, const 
                     bool done = false;
                     if (l_head[n] < 0) {  // nash.rs:66-79 terminal_value
                         const int fn = l_flat[n];
-                        const float u = hero == 0 ? g.nodes[fn].payoff0 : g.payoff1[fn];
+                        float u = hero == 0 ? g.nodes[fn].payoff0 : g.payoff1[fn];
+                        if (g.nodes[fn].turn == TURN_CHANCE) {  // an unexpanded chance node (subgame): V(I) of the nearest non-chance ancestor
+                            int anc = n;
+                            do { anc = l_parent[anc]; } while (anc >= 0 && g.nodes[l_flat[anc]].turn == TURN_CHANCE);
+                            u = anc >= 0 ? s_pay[g.nodes[l_flat[anc]].info] : 0.0f;
+                        }
                         ret = s_rel[sp] / s_smp[sp] * u;
                         done = true;
                     } else if (s_it[sp] < 0) {
@@ -817,7 +825,8 @@ __global__ void table_reset_kernel(rbp_encounter_t* table, int n) {
 // blueprint (regret and weight floored at EPSILON); `update_regret` reads that value and then `mut_regret` creates the local edge from
 // `blueprint.warmstart` and overwrites its regret; `update_weight` then finds the edge locally with the warmstart weight.  So every
 // world's table starts at {weight: averaged policy * k * (k + 1) / 2, regret: max(blueprint regret, EPS), payoff 0, visits 0} and an
-// edge with visits = 0 reads `fb_weight` = max(blueprint weight, EPS) instead of its own weight.  One thread per infoset.
+// edge with visits = 0 reads `fb_weight` = max(blueprint weight, EPS) instead of its own weight (and, for the V(I) of a chance leaf, the
+// blueprint's payoff, second half of `fb_weight`).  One thread per infoset.
 __global__ void __launch_bounds__(128)
 subgame_seed_kernel(DevGame g, const rbp_encounter_t* __restrict__ blueprint, float k, int worlds, rbp_encounter_t* __restrict__ table, float* __restrict__ fb_weight) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -834,6 +843,7 @@ subgame_seed_kernel(DevGame g, const rbp_encounter_t* __restrict__ blueprint, fl
         e.visits = 0u;
         for (int wd = 0; wd < worlds; ++wd) table[(size_t)wd * g.n_rows + row + a] = e;
         fb_weight[row + a] = w[a];
+        fb_weight[g.n_rows + row + a] = blueprint[row + a].payoff;  // world/profile.rs:133-138: cum_payoff falls through unfloored
     }
 }
 
@@ -866,7 +876,7 @@ struct rbp_solver {
     std::vector<cudaEvent_t> events;
     // subgame (rbp_subgame_*): `table` holds sub_worlds x n_rows rows, one table per world (WorldInfo(world, info) keys)
     int sub_worlds = 0, sub_world = 0, sub_entry_plus1 = 0;
-    float* fb_weight = nullptr;  // [n_rows] the blueprint's weights, read for edges the subgame has not written yet
+    float* fb_weight = nullptr;  // [2][n_rows] the blueprint's weights (floored) and payoffs, read for edges the subgame has not written yet
 };
 static inline rbp_encounter_t* tbl(const rbp_solver* s) { return s->table + (size_t)s->sub_world * (size_t)s->game.n_rows; }
 
@@ -1065,7 +1075,7 @@ int rbp_solver_create(int game, int regret, int weight, int sampling, int fold_m
     if ((st = alloc(s, (size_t)d.n_infos * kMaxActions, &s->cfv))) return fail(st);
     if ((st = alloc(s, (size_t)d.n_infos, &s->br))) return fail(st);
     if ((st = alloc(s, 1, &s->expl))) return fail(st);
-    s->sample_smem = (size_t)d.n_infos * (3 * kMaxActions * sizeof(float) + 10 * sizeof(uint32_t));
+    s->sample_smem = (size_t)d.n_infos * (3 * kMaxActions * sizeof(float) + 10 * sizeof(uint32_t) + sizeof(float));
     if (cudaFuncSetAttribute(mccfr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sample_smem) != cudaSuccess)
         return fail(RBP_ERR_CUDA);
     int max_a = 1;
@@ -1384,12 +1394,6 @@ int walk_entry(const FlatGame& G, int c0, int c1, const std::vector<int>& path_c
     }
     return node;
 }
-bool reaches_chance(const FlatGame& G, int node) {
-    const FlatNode& nd = G.nodes[node];
-    if (nd.turn == TURN_CHANCE) return true;
-    for (int c = 0; c < nd.n_child; ++c) if (reaches_chance(G, nd.first_child + c)) return true;
-    return false;
-}
 }  // namespace
 
 extern "C" {
@@ -1464,10 +1468,6 @@ int rbp_subgame_entries(int game, int external, int worlds, const int32_t* world
         }
         const int node = walk_entry(G, hole[0], hole[1], steps, is_card);
         if (node < 0) { set_last_error("subgame: the restricted entry state is not in the game tree"); return RBP_ERR_INVALID; }
-        if (reaches_chance(G, node)) {
-            set_last_error("subgame: a chance node is reachable from the entry state; depth-limited frontiers (DepthGame with an origin) are not built");
-            return RBP_ERR_INVALID;
-        }
         if (cards16) { cards16[2 * w] = hole[0]; cards16[2 * w + 1] = hole[1]; }
         if (nodes8) nodes8[w] = node;
         if (info_keys8) info_keys8[w] = G.nodes[node].info_key;
@@ -1562,7 +1562,7 @@ int rbp_subgame_create(rbp_solver_t* blueprint, int external, int worlds, const 
     if (cudaSetDevice(local->device) != cudaSuccess) return fail(RBP_ERR_CUDA);
     rbp_encounter_t* big = nullptr;
     if ((st = alloc(local, (size_t)worlds * G.n_rows, &big))) return fail(st);
-    if ((st = alloc(local, (size_t)G.n_rows, &local->fb_weight))) return fail(st);
+    if ((st = alloc(local, (size_t)2 * G.n_rows, &local->fb_weight))) return fail(st);  // [weights | payoffs]
     // the blueprint's rows: a host copy for the read-outs, a device copy (on the local stream) to seed from
     g->blueprint_rows.resize(G.n_rows);
     if (cudaStreamSynchronize(blueprint->stream) != cudaSuccess) return fail(RBP_ERR_CUDA);

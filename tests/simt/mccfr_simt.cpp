@@ -150,7 +150,7 @@ void* simt_subgame_create(void* blueprint, int worlds, uint64_t seed) {
     s->hyper = bp->hyper;
     s->worlds = worlds;
     s->table.assign((size_t)worlds * s->G.n_rows, rbp_encounter_t{0.0f, 0.0f, 0.0f, 0u});
-    s->fb.assign(s->G.n_rows, 0.0f);
+    s->fb.assign((size_t)2 * s->G.n_rows, 0.0f);  // [weights | payoffs]
     const DevGame d = s->d;
     const rbp_encounter_t* src = bp->table.data();
     rbp_encounter_t* dst = s->table.data();

@@ -80,12 +80,16 @@ def test_host_entries_equal_the_oracle(oracle, rbp):
     assert n > 5000
 
 
-def test_leduc_first_round_needs_the_frontier(rbp):
-    # from a first-round state the board deal (a chance node) is reachable: `WorldEncoder::branches` would stop there and the reference's
-    # depth-limited machinery takes over — not built, and refused instead of silently truncated
-    with pytest.raises(rbp.RbpError):
-        rbp.subgame.entries("leduc", 1, None, 2, (0, 3), ())
-    rbp.subgame.entries("leduc", 1, None, 2, (0, 3), (1, 1, 2))                       # second round: fine
+def test_leduc_first_round_stops_at_the_board_deal(oracle, rbp):
+    # `WorldEncoder::branches` (world/encoder.rs:97-106) does not expand chance nodes: from a first-round entry the tree ends at the board deal,
+    # and `terminal_value` (mccfr/src/strategy/nash.rs:66-79) gives such a leaf the stored V(I) of the decision node above it
+    bp = oracle.OracleSolver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=3).step(4096)
+    cards, nodes, keys = rbp.subgame.entries("leduc", 1, None, 2, (0, 3), ())        # accepted by the library's host half
+    sg = oracle.OracleSubgame(bp, 1, None, [0.5, 0.5], (0, 3), (), seed=2).step(2000)
+    assert cards[0] == sg.entry(0) and int(keys[0]) == sg.entry_key(0)
+    rows = np.concatenate([sg.profile_rows(w) for w in range(2)])
+    assert len(rows) > 0 and ((rows["info_key"] >> 1) & 3 == 0).all()                 # only first-round infosets (no board) were ever written
+    assert np.isfinite(rows["regret"]).all() and np.abs(rows["payoff"]).max() > 0.0   # the chance leaves carried the blueprint's V(I)
 
 
 def subpolicy(sg, worlds, rank, hist, action):
@@ -194,7 +198,8 @@ def digest(rows):
 def pin_cases(oracle):
     out = {}
     for game, epochs, external, cards, path, worlds in (("kuhn", 4096, 1, (2, 5), (), 2), ("kuhn", 4096, 0, (0, 3), (0,), 3),
-                                                        ("leduc", 8192, 1, (1, 4), (0, 0, 1), 2), ("leduc", 8192, 0, (5, 2), (1, 1, 0, 0), 2)):
+                                                        ("leduc", 8192, 1, (1, 4), (0, 0, 1), 2), ("leduc", 8192, 0, (5, 2), (1, 1, 0, 0), 2),
+                                                        ("leduc", 8192, 1, (0, 3), (), 2), ("leduc", 8192, 0, (4, 1), (1,), 3)):
         bp = oracle.OracleSolver(game, "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(epochs)
         reach = [0.0, 0.0, 0.0]
         for c in range(6):

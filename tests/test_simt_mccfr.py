@@ -70,6 +70,8 @@ def test_training_kernels_under_the_shim_equal_the_oracle(simt, oracle, game, re
     ("kuhn", 300, 0, (4, 1), (0, 1), 2, 200),
     ("leduc", 8192, 1, (1, 4), (0, 0, 1), 2, 40),    # second betting round after check-check and the board
     ("leduc", 8192, 0, (5, 2), (1, 1, 0, 0), 2, 40),
+    ("leduc", 8192, 1, (0, 3), (), 2, 60),           # first round: the tree stops at the board deal, valued by V(I) of the node above it
+    ("leduc", 200, 0, (4, 1), (1,), 2, 60),
 ])
 def test_subgame_kernels_under_the_shim_equal_the_oracle(simt, oracle, rbp, game, epochs, external, cards, path, worlds, steps):
     o_bp = oracle.OracleSolver(game, "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(epochs)

@@ -21,6 +21,8 @@ CASES = [
     ("kuhn", 64, 1, (1, 0), (), 1, 500),               # one world, barely trained blueprint (most rows fall through)
     ("leduc", 8192, 1, (1, 4), (0, 0, 1), 2, 3000),    # second betting round after check-check and the board
     ("leduc", 8192, 0, (5, 2), (1, 1, 0, 0), 2, 3000),
+    ("leduc", 8192, 1, (0, 3), (), 2, 3000),           # first round: the tree stops at the board deal (chance leaves worth the stored V(I))
+    ("leduc", 8192, 0, (4, 1), (1,), 3, 3000),
 ]
 
 
@@ -81,8 +83,10 @@ def test_kuhn_subgame_nash_on_device(rbp, oracle):
 
 def test_spend_and_refusals(rbp, oracle):
     bp = rbp.Solver("leduc", "FlooredRegret", "LinearWeight", "ExternalSampling", batch=1, seed=7).step(256)
-    with pytest.raises(rbp.RbpError):                                                 # first round: the board deal is reachable
-        rbp.subgame.WorldSolver(bp, 1, (None, [1.0]), (0, 3), ())
+    with pytest.raises(rbp.RbpError):                                                 # the path ends at the board deal: not a decision node
+        rbp.subgame.WorldSolver(bp, 1, (None, [1.0]), (0, 3), (1, 1))
+    with pytest.raises(rbp.RbpError):                                                 # the same card twice
+        rbp.subgame.WorldSolver(bp, 1, (None, [1.0]), (3, 3), ())
     sg = rbp.subgame.WorldSolver(bp, 1, (None, [0.5, 0.5]), (0, 3), (1, 1, 2))
     n, dt = sg.spend(0.05)
     assert n >= 8 and dt >= 0.05 and sg.info()["t"] == n
